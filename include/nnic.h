@@ -1,0 +1,140 @@
+/*
+ * nnic.h -- C ABI of libnnic.so, the B200 (sm_100a) implementation of the inference hot path of
+ * AlexFuster/Neural_network_image_compression's tf2_0 codec.
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python call surface of
+ * tf2_0/src/encoder.py, decoder.py and utils.py.  Every entry point below names the reference
+ * call it replaces (paths relative to the reference root).  Plain pointers and sizes only; no
+ * C++ exception crosses this boundary; every function returns 0 on success or a negative
+ * nnic_status, and nnic_last_error() gives the text for the most recent failure on a handle.
+ *
+ * Threading: a handle is bound to one CUDA device and is not thread-safe.  One handle per GPU.
+ * Memory kinds: NNIC_MEM_HOST pointers are ordinary host memory (pageable or pinned); the call
+ * copies in/out and returns after the result is in the caller's buffer.  NNIC_MEM_DEVICE pointers
+ * are device memory on the handle's device; the call only enqueues work on `stream` and returns.
+ */
+#ifndef NNIC_H_
+#define NNIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef struct nnic_handle nnic_t;
+
+enum nnic_status {
+  NNIC_OK = 0,
+  NNIC_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, bad enum */
+  NNIC_ERR_SHAPE = -2,         /* shape not supported by the requested arithmetic mode */
+  NNIC_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see nnic_last_error */
+  NNIC_ERR_NO_WEIGHTS = -4,    /* a network needed by the call has unset layers */
+  NNIC_ERR_NO_DEVICE = -5      /* no usable sm_100 device */
+};
+
+enum nnic_mem_kind { NNIC_MEM_HOST = 0, NNIC_MEM_DEVICE = 1 };
+
+/* The four networks (tf2_0/src/utils.py:15-28: ProClass.models[0] = 'Y', models[1] = 'CbCr',
+ * one ProClass for Encoder and one for Decoder). */
+enum nnic_weight_set { NNIC_SET_ENC_Y = 0, NNIC_SET_ENC_CBCR = 1, NNIC_SET_DEC_Y = 2, NNIC_SET_DEC_CBCR = 3 };
+
+/* Layer index inside a network, in call order (encoder.py:10-17: conv1, conv2, conv3, conv4, conv8;
+ * decoder.py:10-17: dconv1, dconv5, dconv6, dconv7, dconv8). */
+enum { NNIC_LAYERS_PER_NET = 5 };
+
+/* Arithmetic of the eight GEMM-shaped layers (conv2/3/4/8, dconv1/5/6/7):
+ *   NNIC_ARITH_TC_SPLIT  tcgen05 tensor cores, fp16 hi+lo split operands (3 MMAs per product),
+ *                        fp32 accumulation in TMEM.  Default.  Needs H and W multiples of 8.
+ *   NNIC_ARITH_SIMT_F32  plain fp32 FFMA kernels (any H, W >= 1).  Cross-check path.
+ * conv1, dconv8, colour, quantise, histogram and pack kernels are fp32/integer in both modes. */
+enum nnic_arith { NNIC_ARITH_TC_SPLIT = 0, NNIC_ARITH_SIMT_F32 = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Replaces: constructing Encoder()/Decoder() (encoder.py:34-36, decoder.py:35-37). */
+int nnic_create(int device, nnic_t** out);
+void nnic_destroy(nnic_t* h);
+const char* nnic_last_error(const nnic_t* h);   /* never NULL; h may be NULL (global message) */
+const char* nnic_version(void);
+int nnic_set_arith(nnic_t* h, int arith);
+int nnic_get_arith(const nnic_t* h);
+/* Number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches). */
+uint64_t nnic_launch_count(const nnic_t* h);
+
+/* ---- weights --------------------------------------------------------------------------------
+ * Replaces: ProClass.load -> Keras load_weights (utils.py:26-28).  `kernel` is in the Keras layout
+ * of the layer (Conv2D [kh,kw,Cin,Cout]; Conv2DTranspose [kh,kw,Cout,Cin]), fp32, host memory;
+ * `bias` is [Cout].  The library keeps its own repacked copies. */
+int nnic_set_weights(nnic_t* h, int set, int layer, const float* kernel, const float* bias);
+
+/* ---- encode ---------------------------------------------------------------------------------
+ * Replaces: Encoder.__call__ (encoder.py:38-47).
+ *   rgb     uint8 [N,H,W,3], C-contiguous
+ *   latent  uint8 [N,ceil(H/8),ceil(W/8),96]; channels 0-31 Y, 32-63 Cb, 64-95 Cr
+ *   prequant optional (may be NULL) float [N,h,w,96]: the clipped encoder output before
+ *            *255/round (what tf.concat(encoded) holds at encoder.py:45) */
+int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, float* prequant,
+                int mem_kind, void* stream);
+
+/* ---- decode ---------------------------------------------------------------------------------
+ * Replaces: Decoder.__call__ (decoder.py:39-48).
+ *   latent  uint8 [N,lh,lw,96]
+ *   rgb     uint8 [N,8*lh,8*lw,3]
+ *   prequant optional (may be NULL) float [N,8*lh,8*lw,3]: clipped RGB in [0,1] before *255/round */
+int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t* rgb, float* prequant,
+                int mem_kind, void* stream);
+
+/* ---- plane-level model calls ----------------------------------------------------------------
+ * Replaces: ProClass.run_model (utils.py:19-24): three single-network calls with weight sets (0,1,1).
+ *   encoder: planes float [3][N,H,W,1] (plane-major) -> out float [3][N,h,w,32], clipped to [0,1]
+ *   decoder: planes float [3][N,lh,lw,32]            -> out float [3][N,8lh,8lw,1], clipped to [0,1] */
+int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W, float* out,
+                            int mem_kind, void* stream);
+int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int lw, float* out,
+                            int mem_kind, void* stream);
+
+/* ---- rate -----------------------------------------------------------------------------------
+ * Replaces: the discrete histogram/entropy block of tf1_13/src/training.py:62-71 (the only
+ * histogram entropy in the reference), applied to the uint8 latent of Encoder.__call__.
+ *   latent        uint8 [N,lh,lw,96]
+ *   H, W          size of the source images (for bits per pixel)
+ *   hist          optional uint32 [N][3][256]   per (image, plane) counts
+ *   entropy_bits  optional float  [N][3]        sum p*(-log(clip(p,1e-5,1))/log 2), bits per symbol
+ *   bpp           optional float  [N]           sum_p entropy*(lh*lw*32)/(H*W)   (this build's definition)
+ *   hist_global   optional uint64 [3][256]      counts summed over the N images; ACCUMULATED into
+ *                                               (caller zeroes it), so calls over micro-batches add up */
+int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, int W, uint32_t* hist,
+              float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream);
+
+/* Entropy of already-reduced counts (e.g. hist_global after the cross-rank allreduce):
+ *   counts uint64 [rows][256] -> entropy_bits float [rows].  Same formula as nnic_rate. */
+int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits,
+                             int mem_kind, void* stream);
+
+/* ---- scratch management ---------------------------------------------------------------------
+ * Activation scratch is grown lazily and reused.  Images beyond `max_planes_in_flight` colour
+ * planes are processed in micro-batches inside one call.  0 = library default. */
+int nnic_set_micro_batch(nnic_t* h, int max_images_in_flight);
+size_t nnic_scratch_bytes(const nnic_t* h);
+
+/* ---- introspection used by the parity tests ----------------------------------------------------
+ * nnic_colour_constants: the fp32 colour matrices the kernels use: (float32)ycbcr_kernel,
+ * (float32)np.linalg.inv(ycbcr_kernel), (float32)ycbcr_off (utils.py:7-9).  Any pointer may be NULL.
+ * nnic_debug_fetch: copy an intermediate activation of the most recent encode (slots 0-3: conv1, conv2,
+ * conv3, conv4+res) or decode (slots 4-7: latent/255, dconv1, dconv5, dconv6+res) micro-batch to host
+ * memory as fp32 [3*nb,H,W,C].  out == NULL returns the element count. */
+void nnic_colour_constants(float* k9, float* kinv9, float* off3);
+long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNIC_H_ */

@@ -1,0 +1,14 @@
+"""B200-native inference hot path of the Neural_network_image_compression tf2_0 codec.
+
+Public surface (mirrors /root/reference/tf2_0/src): Encoder, Decoder, ProClass, plus rate().
+All arithmetic runs in libnnic.so (hand-written sm_100a CUDA); there is no CPU fallback.
+"""
+from . import weights
+from ._lib import Handle, NnicError, colour_constants, load_library
+from .decoder import Decoder
+from .encoder import Encoder
+from .rate import Rate, entropy_from_counts, rate
+from .utils import ProClass
+
+__all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "Rate", "entropy_from_counts",
+           "weights", "colour_constants", "load_library"]

@@ -1,0 +1,94 @@
+// Host-side launch interface of the libnnic kernels.  Everything here enqueues on `stream` and
+// returns the cudaError_t of the launch.  Layout conventions:
+//   plane batches are plane-major: P = 3N, p = plane*N + n; planes p < n_split use weight set 0
+//   (the 'Y' network), the others weight set 1 ('CbCr')  -- reference tf2_0/src/utils.py:19-24.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace nnic {
+
+struct ColourConsts {
+  float k[3][3];     // RGB -> YCbCr rows   (float)(ycbcr_kernel)      utils.py:7
+  float kinv[3][3];  // YCbCr -> RGB rows   (float)(inv(ycbcr_kernel)) utils.py:8
+  float off[3];      // (float)(ycbcr_off)                             utils.py:9
+};
+const ColourConsts& colour_consts();
+
+// ---- conv1: [colour +] Conv2D(1->32, 5x5, s2, SAME) + bias + leaky ----------------------------
+// in_rgb: u8 [N,H,W,3] (colour transform fused) or in_planes: f32 [3N,H,W,1].  Output [3N,Ho,Wo,32]
+// as split fp16 (out_hi/out_lo) or fp32 (out_f32).  w: [2][25][32] tap-major, bias [2][32].
+cudaError_t launch_conv1(const uint8_t* in_rgb, const float* in_planes, int N, int H, int W,
+                         const float* w, const float* bias, __half* out_hi, __half* out_lo,
+                         float* out_f32, cudaStream_t stream);
+
+// ---- generic fp32 FFMA convolution over a tap program (cross-check path) ----------------------
+// in f32 [P,Hi,Wi,CIN], out f32 [P,Ho,Wo,COUT]; w [2][ntaps_total][CIN][COUT]; bias [2][COUT];
+// res optional f32 [P,Ho,Wo,COUT] added after the activation; Hp x Wp = phase grid.
+cudaError_t launch_simt_conv(int cin, int cout, const float* in, int P, int Hi, int Wi, float* out,
+                             int Ho, int Wo, int Hp, int Wp, const float* w, int ntaps_total,
+                             const float* bias, const float* res, const SimtJobs& jobs, int n_split,
+                             int clamp01, cudaStream_t stream);
+
+// ---- dconv8: Conv2DTranspose(64->1, 5x5, s2, SAME) + bias + leaky + clip, then
+//      convert_to_rgb + clip + *255 + round + uint8 pack, all three planes of an image per block ---
+// input [3N,Hi,Wi,64] split fp16 or f32; w [2][25][64] tap-major; bias [2][1].
+// Outputs (each optional): rgb u8 [N,2Hi,2Wi,3]; prequant f32 [N,2Hi,2Wi,3]; planes f32 [3][N,2Hi,2Wi,1].
+cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float* in_f32, int N, int Hi,
+                          int Wi, const float* w, const float* bias, uint8_t* rgb, float* prequant,
+                          float* planes, cudaStream_t stream);
+
+// ---- latent u8 [N,lh,lw,96] -> /255 -> planes [3N,lh,lw,32] (split fp16 or f32) -----------------
+cudaError_t launch_latent_expand(const uint8_t* latent, int N, int lh, int lw, __half* out_hi,
+                                 __half* out_lo, float* out_f32, cudaStream_t stream);
+// f32 -> split fp16, elementwise (count elements, multiple of 4)
+cudaError_t launch_f32_to_split(const float* in, size_t count, __half* out_hi, __half* out_lo,
+                                cudaStream_t stream);
+// clipped f32 planes [3N,lh,lw,32] -> u8 latent [N,lh,lw,96] (+ optional f32 prequant [N,lh,lw,96])
+cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t* latent, float* prequant,
+                            cudaStream_t stream);
+
+// ---- rate ---------------------------------------------------------------------------------------
+// hist u32 [N][3][256] must be zeroed by the caller (launch_hist adds into it).
+cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist,
+                        cudaStream_t stream);
+cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* hist_global,
+                               cudaStream_t stream);
+// entropy[N][3] from hist u32; bpp[N] = sum_p entropy * symbols_per_plane / pixels  (optional)
+cudaError_t launch_entropy_u32(const uint32_t* hist, int N, float symbols_per_plane, float pixels,
+                               float* entropy, float* bpp, cudaStream_t stream);
+cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float* entropy,
+                               cudaStream_t stream);
+
+// ---- tensor-core convolution (tc_conv.cu) -------------------------------------------------------
+enum TcOutMode { TC_OUT_SPLIT = 0, TC_OUT_F32 = 1, TC_OUT_QUANT = 2 };
+
+struct TcLayerParams {
+  int njobs;
+  TcJob jobs[MAX_JOBS];
+  int P, n_split;
+  int Hp, Wp;                 // phase grid (output pixels per phase)
+  int Ho, Wo, out_stride;     // output tensor geometry [P,Ho,Wo,COUT]; pixel = (Y*out_stride+oy, X*out_stride+ox)
+  int rows_per_set;           // rows of the weight matrix per weight set
+  float inv_scale[2];         // 2^-(ka+kw) per weight set
+  const float* bias;          // [2][COUT]
+  const __half* res_hi;       // optional residual, split fp16 [P,Ho,Wo,COUT]
+  const __half* res_lo;
+  int out_mode;
+  __half* out_hi;             // TC_OUT_SPLIT
+  __half* out_lo;
+  float* out_f32;             // TC_OUT_F32: [P,Ho,Wo,COUT]
+  uint8_t* out_u8;            // TC_OUT_QUANT: latent [N,Ho,Wo,96] (COUT == 32), N = P/3
+  float* out_prequant;        // TC_OUT_QUANT, optional: f32 [N,Ho,Wo,96]
+};
+
+// row_bytes = bytes of one A row (64 or 128); cout = 32 or 64.
+cudaError_t launch_tc_conv(int row_bytes, int cout, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                           const CUtensorMap& w_hi, const CUtensorMap& w_lo, const TcLayerParams& prm,
+                           int num_sms, int* error_flag, cudaStream_t stream);
+
+}  // namespace nnic

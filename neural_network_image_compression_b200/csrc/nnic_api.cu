@@ -1,0 +1,849 @@
+// C ABI of libnnic.so (see include/nnic.h): handle, weight repacking, scratch arena, and the
+// layer-by-layer orchestration of the encode / decode / rate paths.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nnic.h"
+#include "kernels.h"
+
+using namespace nnic;
+
+namespace {
+
+// ---- static layer tables (reference tf2_0/src/encoder.py:10-17, decoder.py:10-17) --------------
+struct LayerSpec { const char* name; int k, s, cin, cout; bool transposed; };
+const LayerSpec kEnc[5] = {{"conv1", 5, 2, 1, 32, false}, {"conv2", 5, 2, 32, 64, false}, {"conv3", 3, 1, 64, 64, false},
+                           {"conv4", 3, 1, 64, 64, false}, {"conv8", 5, 2, 64, 32, false}};
+const LayerSpec kDec[5] = {{"dconv1", 5, 2, 32, 64, true}, {"dconv5", 3, 1, 64, 64, true}, {"dconv6", 3, 1, 64, 64, true},
+                           {"dconv7", 5, 2, 64, 64, true}, {"dconv8", 5, 2, 64, 1, true}};
+inline const LayerSpec& spec_of(int set, int layer) { return set < 2 ? kEnc[layer] : kDec[layer]; }
+
+thread_local std::string g_global_error = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+// Per GEMM-shaped layer: the tap program and the device weight matrices of both weight sets.
+struct TcLayer {
+  int row_bytes = 128, cout = 64, kslab = 64;
+  int njobs = 1;
+  TcJob jobs[MAX_JOBS];
+  int rows_per_set = 0;
+  float inv_scale[2] = {1.f, 1.f};
+  __half* w_hi = nullptr;      // [2][rows_per_set][kslab]
+  __half* w_lo = nullptr;
+  float* bias = nullptr;       // [2][cout]
+  CUtensorMap map_w_hi, map_w_lo;
+  bool parity_view = false;    // input read through the [2C, W/2, 2, H/2, P] view (stride-2 convs)
+  int out_stride = 1;
+};
+struct SimtLayer {
+  float* w = nullptr;          // [2][k*k][cin][cout]
+  float* bias = nullptr;       // [2][cout]
+};
+
+}  // namespace
+
+struct nnic_handle {
+  int device = 0;
+  int num_sms = 148;
+  int arith = NNIC_ARITH_TC_SPLIT;
+  std::string err;
+  uint64_t launches = 0;
+  int micro_batch = 0;
+  EncodeTiledFn encode_tiled = nullptr;
+  int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
+  int* error_flag_dev = nullptr;
+
+  // host copies of the Keras-layout weights
+  std::vector<float> kernel[4][5], bias[4][5];
+  bool have[4][5] = {};
+  bool dirty_enc = true, dirty_dec = true;
+
+  // device weights: index 0 = encoder, 1 = decoder
+  float* w_edge[2] = {nullptr, nullptr};   // conv1 [2][25][32] / dconv8 [2][25][64]
+  float* b_edge[2] = {nullptr, nullptr};   // [2][32] / [2][1]
+  TcLayer tc[2][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7
+  SimtLayer simt[2][4];
+
+  // scratch arena
+  DevBuf arena;
+  size_t arena_used = 0;
+  DevBuf rate_scratch;
+
+  // debug: tensors of the most recent encode/decode micro-batch
+  struct Dbg { const __half* hi; const __half* lo; const float* f32; size_t count; };
+  Dbg dbg[8] = {};
+};
+
+namespace {
+
+int fail(nnic_t* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_global_error = buf;
+  return code;
+}
+#define CK(h, call)                                                                                    \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CKL(h, call)          \
+  do {                        \
+    CK(h, call);              \
+    (h)->launches++;          \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_buf(nnic_t* h, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes) return 0;
+  if (b.ptr) { CK(h, cudaDeviceSynchronize()); CK(h, cudaFree(b.ptr)); b.ptr = nullptr; b.bytes = 0; }
+  size_t want = bytes + bytes / 8 + (1 << 20);
+  CK(h, cudaMalloc(&b.ptr, want));
+  b.bytes = want;
+  return 0;
+}
+void* arena_take(nnic_t* h, size_t bytes) {
+  size_t off = (h->arena_used + 1023) & ~(size_t)1023;
+  h->arena_used = off + bytes;
+  return static_cast<uint8_t*>(h->arena.ptr) + off;
+}
+inline size_t pad1k(size_t b) { return (b + 1023) & ~(size_t)1023; }
+
+void same_pad(int in, int k, int s, int& out, int& before) {
+  out = (in + s - 1) / s;
+  int tot = (out - 1) * s + k - in;
+  if (tot < 0) tot = 0;
+  before = tot / 2;
+}
+
+// ---- tensor maps ---------------------------------------------------------------------------------
+int make_map(nnic_t* h, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box, int row_bytes) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = h->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, NNIC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+// activation view [inner, X, PY, Y, P] of a split-fp16 tensor [P,H,W,C]
+int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, int W, int C, bool parity, int kslab,
+                 int row_bytes) {
+  cuuint64_t dims[5], strides[4];
+  if (!parity) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = P;
+    strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)W * C * 2;
+    strides[3] = (cuuint64_t)H * W * C * 2;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = P;
+    strides[0] = (cuuint64_t)2 * C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)2 * W * C * 2;
+    strides[3] = (cuuint64_t)H * W * C * 2;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)kslab, 8, 1, 16, 1};
+  return make_map(h, map, const_cast<__half*>(base), 5, dims, strides, box, row_bytes);
+}
+
+// ---- weight repacking ----------------------------------------------------------------------------
+// Keras kernel element for GEMM purposes: weight from input channel ci to output channel co at tap (a,b).
+inline float kval(const LayerSpec& sp, const std::vector<float>& kern, int a, int b, int ci, int co) {
+  if (!sp.transposed) return kern[(((size_t)a * sp.k + b) * sp.cin + ci) * sp.cout + co];   // [kh,kw,Cin,Cout]
+  return kern[(((size_t)a * sp.k + b) * sp.cout + co) * sp.cin + ci];                        // [kh,kw,Cout,Cin]
+}
+
+void build_tc_program(const LayerSpec& sp, TcLayer& L) {
+  L.cout = sp.cout;
+  L.parity_view = !sp.transposed && sp.s == 2;
+  L.out_stride = sp.transposed ? sp.s : 1;
+  memset(L.jobs, 0, sizeof L.jobs);
+  if (!sp.transposed && sp.s == 1) {            // conv3, conv4
+    L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
+    TcJob& j = L.jobs[0]; j.nsteps = 9;
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+      TcStep& s = j.steps[a * 3 + b];
+      s.dy = a - 1; s.dx = b - 1; s.py = 0; s.koff = 0; s.w_row = (a * 3 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
+    }
+    L.rows_per_set = 9 * sp.cout;
+  } else if (!sp.transposed && sp.s == 2 && sp.cin == 32) {   // conv2: column taps paired in one 64-wide slab
+    L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
+    TcJob& j = L.jobs[0]; j.nsteps = 15;
+    for (int a = 0; a < 5; ++a) for (int jj = -1; jj <= 1; ++jj) {
+      TcStep& s = j.steps[a * 3 + jj + 1];
+      s.dy = (a - 1) >> 1; s.py = (a - 1) & 1; s.dx = jj; s.koff = 0; s.w_row = (a * 3 + jj + 1) * sp.cout;
+      s.ks_begin = jj == -1 ? 2 : 0; s.ks_end = 4;
+    }
+    L.rows_per_set = 15 * sp.cout;
+  } else if (!sp.transposed && sp.s == 2) {     // conv8
+    L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
+    TcJob& j = L.jobs[0]; j.nsteps = 25;
+    for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) {
+      TcStep& s = j.steps[a * 5 + b];
+      s.dy = (a - 1) >> 1; s.py = (a - 1) & 1; s.dx = (b - 1) >> 1; s.koff = ((b - 1) & 1) * 64;
+      s.w_row = (a * 5 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
+    }
+    L.rows_per_set = 25 * sp.cout;
+  } else if (sp.transposed && sp.s == 1) {      // dconv5, dconv6: out[o] = sum_a x[o+1-a] K[a]
+    L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
+    TcJob& j = L.jobs[0]; j.nsteps = 9;
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+      TcStep& s = j.steps[a * 3 + b];
+      s.dy = 1 - a; s.dx = 1 - b; s.py = 0; s.koff = 0; s.w_row = (a * 3 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
+    }
+    L.rows_per_set = 9 * sp.cout;
+  } else {                                      // dconv1 (Cin 32), dconv7 (Cin 64): four output parity phases
+    L.row_bytes = sp.cin * 2; L.kslab = sp.cin; L.njobs = 4;
+    for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
+      TcJob& j = L.jobs[py * 2 + px]; j.nsteps = 0; j.out_oy = py; j.out_ox = px;
+      for (int a = (py + 1) & 1; a < 5; a += 2) for (int b = (px + 1) & 1; b < 5; b += 2) {
+        TcStep& s = j.steps[j.nsteps++];
+        s.dy = (py + 1 - a) / 2; s.dx = (px + 1 - b) / 2; s.py = 0; s.koff = 0; s.w_row = (a * 5 + b) * sp.cout;
+        s.ks_begin = 0; s.ks_end = sp.cin / 16;
+      }
+    }
+    L.rows_per_set = 25 * sp.cout;
+  }
+}
+
+// value of the TC weight matrix of `sp` at (row, col) for Keras kernel `kern`
+float tc_weight_at(const LayerSpec& sp, const std::vector<float>& kern, int row, int col) {
+  const int tile = row / sp.cout, co = row % sp.cout;
+  if (!sp.transposed && sp.s == 2 && sp.cin == 32) {       // conv2 paired slabs
+    const int a = tile / 3, jj = tile % 3 - 1, px = col / 32, ci = col % 32;
+    const int b = 2 * jj + 1 + px;
+    if (b < 0 || b > 4) return 0.0f;
+    return kval(sp, kern, a, b, ci, co);
+  }
+  const int a = tile / sp.k, b = tile % sp.k;
+  return kval(sp, kern, a, b, col, co);
+}
+
+int upload(nnic_t* h, void** dst, const void* src, size_t bytes) {
+  if (!*dst) CK(h, cudaMalloc(dst, bytes));
+  CK(h, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
+  bool& dirty = net == 0 ? h->dirty_enc : h->dirty_dec;
+  if (!dirty) return 0;
+  const int set0 = net * 2;
+  for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < 5; ++l)
+      if (!h->have[set0 + s][l])
+        return fail(h, NNIC_ERR_NO_WEIGHTS, "weights of set %d layer %s are not set", set0 + s, spec_of(set0, l).name);
+  CK(h, cudaDeviceSynchronize());
+  // edge layer (conv1 / dconv8): tap-major fp32; both Keras layouts already are [tap][..] with the unit dim dropped
+  {
+    const int l = net == 0 ? 0 : 4;
+    const LayerSpec& sp = spec_of(set0, l);
+    const int per = sp.k * sp.k * (net == 0 ? sp.cout : sp.cin);
+    const int nb = sp.cout;
+    std::vector<float> w(2 * per), b(2 * nb);
+    for (int s = 0; s < 2; ++s) {
+      memcpy(&w[s * per], h->kernel[set0 + s][l].data(), per * sizeof(float));
+      memcpy(&b[s * nb], h->bias[set0 + s][l].data(), nb * sizeof(float));
+    }
+    if (int rc = upload(h, (void**)&h->w_edge[net], w.data(), w.size() * 4)) return rc;
+    if (int rc = upload(h, (void**)&h->b_edge[net], b.data(), b.size() * 4)) return rc;
+  }
+  for (int gi = 0; gi < 4; ++gi) {
+    const int l = net == 0 ? gi + 1 : gi;
+    const LayerSpec& sp = spec_of(set0, l);
+    // --- fp32 tap-major copies for the FFMA path: [set][tap][ci][co]
+    {
+      const size_t per = (size_t)sp.k * sp.k * sp.cin * sp.cout;
+      std::vector<float> w(2 * per), b(2 * sp.cout);
+      for (int s = 0; s < 2; ++s) {
+        const std::vector<float>& kern = h->kernel[set0 + s][l];
+        for (int a = 0; a < sp.k; ++a) for (int bb = 0; bb < sp.k; ++bb)
+          for (int ci = 0; ci < sp.cin; ++ci) for (int co = 0; co < sp.cout; ++co)
+            w[s * per + (((size_t)a * sp.k + bb) * sp.cin + ci) * sp.cout + co] = kval(sp, kern, a, bb, ci, co);
+        memcpy(&b[s * sp.cout], h->bias[set0 + s][l].data(), sp.cout * sizeof(float));
+      }
+      if (int rc = upload(h, (void**)&h->simt[net][gi].w, w.data(), w.size() * 4)) return rc;
+      if (int rc = upload(h, (void**)&h->simt[net][gi].bias, b.data(), b.size() * 4)) return rc;
+    }
+    // --- tensor-core matrices: fp16 hi/lo of w * 2^kexp, [set][rows][kslab]
+    TcLayer& L = h->tc[net][gi];
+    build_tc_program(sp, L);
+    const size_t per = (size_t)L.rows_per_set * L.kslab;
+    std::vector<__half> whi(2 * per), wlo(2 * per);
+    std::vector<float> b(2 * sp.cout);
+    for (int s = 0; s < 2; ++s) {
+      const std::vector<float>& kern = h->kernel[set0 + s][l];
+      float maxabs = 0.f;
+      for (float v : kern) maxabs = fmaxf(maxabs, fabsf(v));
+      int kexp = 0;
+      if (maxabs > 0.f && std::isfinite(maxabs)) {
+        kexp = (int)floorf(log2f(32768.0f / maxabs));
+        if (kexp < -14) kexp = -14;
+        if (kexp > 24) kexp = 24;
+      }
+      const float scale = ldexpf(1.0f, kexp);
+      L.inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
+      for (int r = 0; r < L.rows_per_set; ++r)
+        for (int c = 0; c < L.kslab; ++c) {
+          const float v = tc_weight_at(sp, kern, r, c) * scale;
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          whi[s * per + (size_t)r * L.kslab + c] = hi;
+          wlo[s * per + (size_t)r * L.kslab + c] = lo;
+        }
+      memcpy(&b[s * sp.cout], h->bias[set0 + s][l].data(), sp.cout * sizeof(float));
+    }
+    if (int rc = upload(h, (void**)&L.w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
+    if (int rc = upload(h, (void**)&L.w_lo, wlo.data(), wlo.size() * sizeof(__half))) return rc;
+    if (int rc = upload(h, (void**)&L.bias, b.data(), b.size() * 4)) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)L.kslab, (cuuint64_t)2 * L.rows_per_set};
+    cuuint64_t strides[1] = {(cuuint64_t)L.kslab * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kslab, (cuuint32_t)L.cout};
+    if (int rc = make_map(h, &L.map_w_hi, L.w_hi, 2, dims, strides, box, L.row_bytes)) return rc;
+    if (int rc = make_map(h, &L.map_w_lo, L.w_lo, 2, dims, strides, box, L.row_bytes)) return rc;
+  }
+  dirty = false;
+  return 0;
+}
+
+// ---- FFMA tap programs ---------------------------------------------------------------------------
+void build_simt_jobs(const LayerSpec& sp, int Hi, int Wi, SimtJobs& J) {
+  memset(&J, 0, sizeof J);
+  if (!sp.transposed) {
+    int Ho, Wo, pt, pl;
+    same_pad(Hi, sp.k, sp.s, Ho, pt);
+    same_pad(Wi, sp.k, sp.s, Wo, pl);
+    J.njobs = 1; J.in_stride = sp.s; J.out_stride = 1;
+    SimtJob& j = J.job[0];
+    for (int a = 0; a < sp.k; ++a) for (int b = 0; b < sp.k; ++b) {
+      SimtTap& t = j.taps[j.ntaps++];
+      t.dy = a - pt; t.dx = b - pl; t.widx = a * sp.k + b;
+    }
+  } else if (sp.s == 1) {
+    J.njobs = 1; J.in_stride = 1; J.out_stride = 1;
+    SimtJob& j = J.job[0];
+    for (int a = 0; a < sp.k; ++a) for (int b = 0; b < sp.k; ++b) {
+      SimtTap& t = j.taps[j.ntaps++];
+      t.dy = 1 - a; t.dx = 1 - b; t.widx = a * sp.k + b;
+    }
+  } else {
+    J.njobs = 4; J.in_stride = 1; J.out_stride = 2;
+    for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
+      SimtJob& j = J.job[py * 2 + px];
+      j.out_oy = py; j.out_ox = px;
+      for (int a = (py + 1) & 1; a < 5; a += 2) for (int b = (px + 1) & 1; b < 5; b += 2) {
+        SimtTap& t = j.taps[j.ntaps++];
+        t.dy = (py + 1 - a) / 2; t.dx = (px + 1 - b) / 2; t.widx = a * 5 + b;
+      }
+    }
+  }
+}
+
+struct Act {          // an activation tensor [P,H,W,C] in one of the two storage forms
+  __half* hi = nullptr; __half* lo = nullptr; float* f32 = nullptr;
+  int H = 0, W = 0, C = 0;
+};
+
+Act take_act(nnic_t* h, bool split, int P, int H, int W, int C) {
+  Act a; a.H = H; a.W = W; a.C = C;
+  const size_t n = (size_t)P * H * W * C;
+  if (split) { a.hi = (__half*)arena_take(h, n * 2); a.lo = (__half*)arena_take(h, n * 2); }
+  else a.f32 = (float*)arena_take(h, n * 4);
+  return a;
+}
+inline size_t act_bytes(bool split, size_t P, size_t H, size_t W, size_t C) {
+  return split ? 2 * pad1k(P * H * W * C * 2) : pad1k(P * H * W * C * 4);
+}
+void record_dbg(nnic_t* h, int slot, const Act& a, int P) {
+  h->dbg[slot] = {a.hi, a.lo, a.f32, (size_t)P * a.H * a.W * a.C};
+}
+
+int check_device_error(nnic_t* h) {
+  if (h->error_flag_host && *h->error_flag_host != 0)
+    return fail(h, NNIC_ERR_CUDA, "tensor-core kernel barrier wait timed out (code %d)", *h->error_flag_host);
+  return 0;
+}
+
+// one GEMM-shaped layer in either arithmetic
+int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, const Act* res, int P, int n_split,
+                   int out_mode, uint8_t* out_u8, float* out_prequant, float* out_f32_planes, cudaStream_t st) {
+  const int l = net == 0 ? gi + 1 : gi;
+  const LayerSpec& sp = spec_of(net * 2, l);
+  int Ho, Wo, Hp, Wp;
+  if (!sp.transposed) { int pt; same_pad(in.H, sp.k, sp.s, Ho, pt); same_pad(in.W, sp.k, sp.s, Wo, pt); Hp = Ho; Wp = Wo; }
+  else { Ho = in.H * sp.s; Wo = in.W * sp.s; Hp = in.H; Wp = in.W; }
+  if (h->arith == NNIC_ARITH_SIMT_F32) {
+    SimtJobs J;
+    build_simt_jobs(sp, in.H, in.W, J);
+    float* dst = out_mode == TC_OUT_F32 && out_f32_planes ? out_f32_planes : out.f32;
+    const int clamp = (net == 0 && gi == 3) ? 1 : 0;
+    CKL(h, launch_simt_conv(sp.cin, sp.cout, in.f32, P, in.H, in.W, dst, Ho, Wo, Hp, Wp, h->simt[net][gi].w, sp.k * sp.k,
+                            h->simt[net][gi].bias, res ? res->f32 : nullptr, J, n_split, clamp, st));
+    return 0;
+  }
+  TcLayer& L = h->tc[net][gi];
+  CUtensorMap ma_hi, ma_lo;
+  if (int rc = make_act_map(h, &ma_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
+  if (int rc = make_act_map(h, &ma_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
+  TcLayerParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.njobs = L.njobs;
+  memcpy(prm.jobs, L.jobs, sizeof L.jobs);
+  prm.P = P; prm.n_split = n_split; prm.Hp = Hp; prm.Wp = Wp; prm.Ho = Ho; prm.Wo = Wo; prm.out_stride = L.out_stride;
+  prm.rows_per_set = L.rows_per_set;
+  prm.inv_scale[0] = L.inv_scale[0]; prm.inv_scale[1] = L.inv_scale[1];
+  prm.bias = L.bias;
+  prm.res_hi = res ? res->hi : nullptr; prm.res_lo = res ? res->lo : nullptr;
+  prm.out_mode = out_mode;
+  prm.out_hi = out.hi; prm.out_lo = out.lo;
+  prm.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
+  prm.out_u8 = out_u8; prm.out_prequant = out_prequant;
+  CKL(h, launch_tc_conv(L.row_bytes, L.cout, ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, prm, h->num_sms, h->error_flag_dev, st));
+  return 0;
+}
+
+int pick_micro_batch(const nnic_t* h, int N, size_t pixels_per_image) {
+  if (h->micro_batch > 0) return h->micro_batch < N ? h->micro_batch : N;
+  const size_t target = (size_t)16 << 20;   // ~16 MP of RGB pixels in flight
+  size_t nb = target / (pixels_per_image ? pixels_per_image : 1);
+  if (nb < 1) nb = 1;
+  if (nb > 21845) nb = 21845;               // 3*nb planes must fit gridDim.y/z
+  return (int)(nb < (size_t)N ? nb : (size_t)N);
+}
+
+// ---- encoder for one micro-batch -----------------------------------------------------------------
+// in: rgb u8 [nb,H,W,3] (device) or f32 planes [3nb,H,W,1] (device).  Outputs are device pointers.
+int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int H, int W, uint8_t* latent,
+                 float* prequant, float* out_planes, cudaStream_t st) {
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const int P = 3 * nb;
+  int H1, W1, H2, W2, H3, W3, t;
+  same_pad(H, 5, 2, H1, t); same_pad(W, 5, 2, W1, t);
+  same_pad(H1, 5, 2, H2, t); same_pad(W1, 5, 2, W2, t);
+  same_pad(H2, 5, 2, H3, t); same_pad(W2, 5, 2, W3, t);
+  const size_t need = act_bytes(split, P, H1, W1, 32) + 3 * act_bytes(split, P, H2, W2, 64) +
+                      (split ? 0 : act_bytes(false, P, H3, W3, 32)) + 8192;
+  size_t base_used = h->arena_used;
+  if (h->arena.bytes < base_used + need) return fail(h, NNIC_ERR_CUDA, "internal: arena too small (%zu < %zu)", h->arena.bytes, base_used + need);
+  Act a1 = take_act(h, split, P, H1, W1, 32);
+  Act a2 = take_act(h, split, P, H2, W2, 64);
+  Act a3 = take_act(h, split, P, H2, W2, 64);
+  Act a4 = take_act(h, split, P, H2, W2, 64);
+  Act a5; a5.H = H3; a5.W = W3; a5.C = 32;
+  CKL(h, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0], h->b_edge[0], a1.hi, a1.lo, a1.f32, st));
+  if (int rc = run_gemm_layer(h, 0, 0, a1, a2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (int rc = run_gemm_layer(h, 0, 1, a2, a3, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (int rc = run_gemm_layer(h, 0, 2, a3, a4, &a2, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (split) {
+    if (out_planes) {
+      if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, out_planes, st)) return rc;
+    } else {
+      if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_QUANT, latent, prequant, nullptr, st)) return rc;
+    }
+  } else {
+    if (out_planes) {
+      if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, out_planes, st)) return rc;
+    } else {
+      a5 = take_act(h, false, P, H3, W3, 32);
+      if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, nullptr, st)) return rc;
+      CKL(h, launch_quantise(a5.f32, nb, H3, W3, latent, prequant, st));
+    }
+  }
+  record_dbg(h, 0, a1, P); record_dbg(h, 1, a2, P); record_dbg(h, 2, a3, P); record_dbg(h, 3, a4, P);
+  h->arena_used = base_used;
+  return 0;
+}
+
+// ---- decoder for one micro-batch -----------------------------------------------------------------
+int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, int lh, int lw, uint8_t* rgb,
+                 float* prequant, float* out_planes, cudaStream_t st) {
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const int P = 3 * nb;
+  const size_t need = act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) +
+                      act_bytes(split, P, 4 * lh, 4 * lw, 64) + 8192;
+  size_t base_used = h->arena_used;
+  if (h->arena.bytes < base_used + need) return fail(h, NNIC_ERR_CUDA, "internal: arena too small (%zu < %zu)", h->arena.bytes, base_used + need);
+  Act d0 = take_act(h, split, P, lh, lw, 32);
+  Act d1 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
+  Act d2 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
+  Act d3 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
+  Act d4 = take_act(h, split, P, 4 * lh, 4 * lw, 64);
+  if (latent) {
+    CKL(h, launch_latent_expand(latent, nb, lh, lw, d0.hi, d0.lo, d0.f32, st));
+  } else if (split) {
+    CKL(h, launch_f32_to_split(planes, (size_t)P * lh * lw * 32, d0.hi, d0.lo, st));
+  } else {
+    d0.f32 = const_cast<float*>(planes);
+  }
+  if (int rc = run_gemm_layer(h, 1, 0, d0, d1, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  CKL(h, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1], h->b_edge[1], rgb, prequant, out_planes, st));
+  record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
+  h->arena_used = base_used;
+  return 0;
+}
+
+size_t enc_act_need(bool split, size_t P, int H, int W) {
+  int H1, W1, H2, W2, H3, W3, t;
+  same_pad(H, 5, 2, H1, t); same_pad(W, 5, 2, W1, t);
+  same_pad(H1, 5, 2, H2, t); same_pad(W1, 5, 2, W2, t);
+  same_pad(H2, 5, 2, H3, t); same_pad(W2, 5, 2, W3, t);
+  return act_bytes(split, P, H1, W1, 32) + 3 * act_bytes(split, P, H2, W2, 64) + act_bytes(false, P, H3, W3, 32) + 16384;
+}
+size_t dec_act_need(bool split, size_t P, int lh, int lw) {
+  return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
+}
+
+int check_tc_shape(nnic_t* h, int H, int W) {
+  if (h->arith == NNIC_ARITH_TC_SPLIT && (H % 8 != 0 || W % 8 != 0))
+    return fail(h, NNIC_ERR_SHAPE, "tensor-core arithmetic needs H and W to be multiples of 8 (got %dx%d); use NNIC_ARITH_SIMT_F32", H, W);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* nnic_version(void) { return "nnic-b200 0.1 (sm_100a)"; }
+
+const char* nnic_last_error(const nnic_t* h) { return h ? h->err.c_str() : g_global_error.c_str(); }
+
+int nnic_create(int device, nnic_t** out) {
+  if (!out) return fail(nullptr, NNIC_ERR_INVALID_ARG, "nnic_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(nullptr, NNIC_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, NNIC_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, NNIC_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, NNIC_ERR_NO_DEVICE, "device %d is sm_%d%d; libnnic is built for sm_100a only", device, prop.major, prop.minor);
+  nnic_t* h = new nnic_t();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  DeviceGuard g(device);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    delete h;
+    return fail(nullptr, NNIC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  }
+  h->encode_tiled = (EncodeTiledFn)fn;
+  e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
+  if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return NNIC_OK;
+}
+
+void nnic_destroy(nnic_t* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  for (int n = 0; n < 2; ++n) {
+    cudaFree(h->w_edge[n]); cudaFree(h->b_edge[n]);
+    for (int i = 0; i < 4; ++i) {
+      cudaFree(h->tc[n][i].w_hi); cudaFree(h->tc[n][i].w_lo); cudaFree(h->tc[n][i].bias);
+      cudaFree(h->simt[n][i].w); cudaFree(h->simt[n][i].bias);
+    }
+  }
+  cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
+  if (h->error_flag_host) cudaFreeHost(h->error_flag_host);
+  delete h;
+}
+
+int nnic_set_arith(nnic_t* h, int arith) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (arith != NNIC_ARITH_TC_SPLIT && arith != NNIC_ARITH_SIMT_F32) return fail(h, NNIC_ERR_INVALID_ARG, "unknown arithmetic %d", arith);
+  h->arith = arith;
+  return NNIC_OK;
+}
+int nnic_get_arith(const nnic_t* h) { return h ? h->arith : NNIC_ERR_INVALID_ARG; }
+uint64_t nnic_launch_count(const nnic_t* h) { return h ? h->launches : 0; }
+int nnic_set_micro_batch(nnic_t* h, int n) { if (!h || n < 0) return NNIC_ERR_INVALID_ARG; h->micro_batch = n; return NNIC_OK; }
+size_t nnic_scratch_bytes(const nnic_t* h) { return h ? h->arena.bytes + h->rate_scratch.bytes : 0; }
+
+void nnic_colour_constants(float* k9, float* kinv9, float* off3) {
+  const ColourConsts& c = colour_consts();
+  if (k9) memcpy(k9, c.k, 9 * sizeof(float));
+  if (kinv9) memcpy(kinv9, c.kinv, 9 * sizeof(float));
+  if (off3) memcpy(off3, c.off, 3 * sizeof(float));
+}
+
+int nnic_set_weights(nnic_t* h, int set, int layer, const float* kernel, const float* bias) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (set < 0 || set > 3 || layer < 0 || layer >= NNIC_LAYERS_PER_NET) return fail(h, NNIC_ERR_INVALID_ARG, "bad set/layer %d/%d", set, layer);
+  if (!kernel || !bias) return fail(h, NNIC_ERR_INVALID_ARG, "kernel/bias is NULL");
+  const LayerSpec& sp = spec_of(set, layer);
+  const size_t nk = (size_t)sp.k * sp.k * sp.cin * sp.cout;
+  h->kernel[set][layer].assign(kernel, kernel + nk);
+  h->bias[set][layer].assign(bias, bias + sp.cout);
+  h->have[set][layer] = true;
+  if (set < 2) h->dirty_enc = true; else h->dirty_dec = true;
+  return NNIC_OK;
+}
+
+int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, float* prequant, int mem_kind,
+                void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!rgb || !latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: NULL buffer");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: non-positive shape %dx%dx%d", N, H, W);
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  if (int rc = check_tc_shape(h, H, W)) return rc;
+  DeviceGuard g(h->device);
+  if (int rc = finalize_weights(h, 0)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const int lh = (H + 7) / 8, lw = (W + 7) / 8;
+  const size_t img_px = (size_t)H * W, lat_px = (size_t)lh * lw;
+  const int mb = pick_micro_batch(h, N, img_px);
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  size_t need = enc_act_need(split, 3 * (size_t)mb, H, W);
+  if (host) need += pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * lat_px * 96 * 4) : 0) + 4096;
+  if (int rc = ensure_buf(h, h->arena, need)) return rc;
+  h->arena_used = 0;
+  uint8_t *d_rgb = nullptr, *d_lat = nullptr; float* d_pre = nullptr;
+  if (host) {
+    d_rgb = (uint8_t*)arena_take(h, mb * img_px * 3);
+    d_lat = (uint8_t*)arena_take(h, mb * lat_px * 96);
+    if (prequant) d_pre = (float*)arena_take(h, mb * lat_px * 96 * 4);
+  }
+  for (int i0 = 0; i0 < N; i0 += mb) {
+    const int nb = (N - i0) < mb ? (N - i0) : mb;
+    const uint8_t* src = rgb + (size_t)i0 * img_px * 3;
+    uint8_t* dst = latent + (size_t)i0 * lat_px * 96;
+    float* pre = prequant ? prequant + (size_t)i0 * lat_px * 96 : nullptr;
+    if (host) {
+      CK(h, cudaMemcpyAsync(d_rgb, src, nb * img_px * 3, cudaMemcpyHostToDevice, st));
+      if (int rc = encode_batch(h, d_rgb, nullptr, nb, H, W, d_lat, d_pre, nullptr, st)) return rc;
+      CK(h, cudaMemcpyAsync(dst, d_lat, nb * lat_px * 96, cudaMemcpyDeviceToHost, st));
+      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre, nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, st)) return rc;
+    }
+  }
+  if (host) { CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
+  return NNIC_OK;
+}
+
+int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t* rgb, float* prequant, int mem_kind,
+                void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!rgb || !latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_decode: NULL buffer");
+  if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_decode: non-positive shape %dx%dx%d", N, lh, lw);
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  if (int rc = finalize_weights(h, 1)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const size_t img_px = (size_t)lh * lw * 64, lat_px = (size_t)lh * lw;
+  const int mb = pick_micro_batch(h, N, img_px);
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  size_t need = dec_act_need(split, 3 * (size_t)mb, lh, lw);
+  if (host) need += pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * img_px * 3 * 4) : 0) + 4096;
+  if (int rc = ensure_buf(h, h->arena, need)) return rc;
+  h->arena_used = 0;
+  uint8_t *d_rgb = nullptr, *d_lat = nullptr; float* d_pre = nullptr;
+  if (host) {
+    d_rgb = (uint8_t*)arena_take(h, mb * img_px * 3);
+    d_lat = (uint8_t*)arena_take(h, mb * lat_px * 96);
+    if (prequant) d_pre = (float*)arena_take(h, mb * img_px * 3 * 4);
+  }
+  for (int i0 = 0; i0 < N; i0 += mb) {
+    const int nb = (N - i0) < mb ? (N - i0) : mb;
+    const uint8_t* src = latent + (size_t)i0 * lat_px * 96;
+    uint8_t* dst = rgb + (size_t)i0 * img_px * 3;
+    float* pre = prequant ? prequant + (size_t)i0 * img_px * 3 : nullptr;
+    if (host) {
+      CK(h, cudaMemcpyAsync(d_lat, src, nb * lat_px * 96, cudaMemcpyHostToDevice, st));
+      if (int rc = decode_batch(h, d_lat, nullptr, nb, lh, lw, d_rgb, d_pre, nullptr, st)) return rc;
+      CK(h, cudaMemcpyAsync(dst, d_rgb, nb * img_px * 3, cudaMemcpyDeviceToHost, st));
+      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre, nb * img_px * 3 * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      if (int rc = decode_batch(h, src, nullptr, nb, lh, lw, dst, pre, nullptr, st)) return rc;
+    }
+  }
+  if (host) { CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
+  return NNIC_OK;
+}
+
+int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W, float* out, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_encoder_planes: NULL buffer");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
+  if (int rc = check_tc_shape(h, H, W)) return rc;
+  DeviceGuard g(h->device);
+  if (int rc = finalize_weights(h, 0)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const int lh = (H + 7) / 8, lw = (W + 7) / 8;
+  const size_t in_elems = (size_t)3 * N * H * W, out_elems = (size_t)3 * N * lh * lw * 32;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  size_t need = enc_act_need(split, 3 * (size_t)N, H, W) + (host ? pad1k(in_elems * 4) + pad1k(out_elems * 4) + 4096 : 0);
+  if (int rc = ensure_buf(h, h->arena, need)) return rc;
+  h->arena_used = 0;
+  const float* d_in = planes; float* d_out = out;
+  if (host) {
+    float* t_in = (float*)arena_take(h, in_elems * 4);
+    d_out = (float*)arena_take(h, out_elems * 4);
+    CK(h, cudaMemcpyAsync(t_in, planes, in_elems * 4, cudaMemcpyHostToDevice, st));
+    d_in = t_in;
+  }
+  if (int rc = encode_batch(h, nullptr, d_in, N, H, W, nullptr, nullptr, d_out, st)) return rc;
+  if (host) {
+    CK(h, cudaMemcpyAsync(out, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (int rc = check_device_error(h)) return rc;
+  }
+  return NNIC_OK;
+}
+
+int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int lw, float* out, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_decoder_planes: NULL buffer");
+  if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
+  DeviceGuard g(h->device);
+  if (int rc = finalize_weights(h, 1)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const size_t in_elems = (size_t)3 * N * lh * lw * 32, out_elems = (size_t)3 * N * lh * lw * 64;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  size_t need = dec_act_need(split, 3 * (size_t)N, lh, lw) + (host ? pad1k(in_elems * 4) + pad1k(out_elems * 4) + 4096 : 0);
+  if (int rc = ensure_buf(h, h->arena, need)) return rc;
+  h->arena_used = 0;
+  const float* d_in = planes; float* d_out = out;
+  if (host) {
+    float* t_in = (float*)arena_take(h, in_elems * 4);
+    d_out = (float*)arena_take(h, out_elems * 4);
+    CK(h, cudaMemcpyAsync(t_in, planes, in_elems * 4, cudaMemcpyHostToDevice, st));
+    d_in = t_in;
+  }
+  if (int rc = decode_batch(h, nullptr, d_in, N, lh, lw, nullptr, nullptr, d_out, st)) return rc;
+  if (host) {
+    CK(h, cudaMemcpyAsync(out, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (int rc = check_device_error(h)) return rc;
+  }
+  return NNIC_OK;
+}
+
+int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, int W, uint32_t* hist, float* entropy_bits,
+              float* bpp, uint64_t* hist_global, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_rate: latent is NULL");
+  if (N <= 0 || lh <= 0 || lw <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_rate: non-positive shape");
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  const size_t lat_bytes = (size_t)N * lh * lw * 96;
+  const size_t hist_bytes = (size_t)N * 768 * 4;
+  size_t need = pad1k(hist_bytes) + pad1k((size_t)N * 3 * 4) + pad1k((size_t)N * 4) + pad1k(768 * 8) + (host ? pad1k(lat_bytes) : 0) + 8192;
+  if (int rc = ensure_buf(h, h->rate_scratch, need)) return rc;
+  uint8_t* base = (uint8_t*)h->rate_scratch.ptr;
+  size_t off = 0;
+  auto take = [&](size_t b) { void* p = base + off; off += pad1k(b); return p; };
+  uint32_t* d_hist = (uint32_t*)take(hist_bytes);
+  float* d_ent = (float*)take((size_t)N * 3 * 4);
+  float* d_bpp = (float*)take((size_t)N * 4);
+  unsigned long long* d_glob = (unsigned long long*)take(768 * 8);
+  const uint8_t* d_lat = latent;
+  if (host) {
+    uint8_t* t = (uint8_t*)take(lat_bytes);
+    CK(h, cudaMemcpyAsync(t, latent, lat_bytes, cudaMemcpyHostToDevice, st));
+    d_lat = t;
+  } else {
+    if (hist) d_hist = hist;
+    if (entropy_bits) d_ent = entropy_bits;
+    if (bpp) d_bpp = bpp;
+    if (hist_global) d_glob = (unsigned long long*)hist_global;
+  }
+  CK(h, cudaMemsetAsync(d_hist, 0, hist_bytes, st));
+  CKL(h, launch_hist(d_lat, N, (size_t)lh * lw, d_hist, st));
+  if (entropy_bits || bpp)
+    CKL(h, launch_entropy_u32(d_hist, N, (float)((size_t)lh * lw * 32), (float)((size_t)H * W), d_ent, d_bpp, st));
+  if (hist_global) {
+    if (host) CK(h, cudaMemcpyAsync(d_glob, hist_global, 768 * 8, cudaMemcpyHostToDevice, st));
+    CKL(h, launch_hist_reduce(d_hist, N, d_glob, st));
+  }
+  if (host) {
+    if (hist) CK(h, cudaMemcpyAsync(hist, d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
+    if (entropy_bits) CK(h, cudaMemcpyAsync(entropy_bits, d_ent, (size_t)N * 3 * 4, cudaMemcpyDeviceToHost, st));
+    if (bpp) CK(h, cudaMemcpyAsync(bpp, d_bpp, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (hist_global) CK(h, cudaMemcpyAsync(hist_global, d_glob, 768 * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+  }
+  return NNIC_OK;
+}
+
+int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!counts || !entropy_bits || rows <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_entropy_from_counts: bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mem_kind == NNIC_MEM_DEVICE) {
+    CKL(h, launch_entropy_u64((const unsigned long long*)counts, rows, entropy_bits, st));
+    return NNIC_OK;
+  }
+  size_t need = pad1k((size_t)rows * 256 * 8) + pad1k((size_t)rows * 4) + 4096;
+  if (int rc = ensure_buf(h, h->rate_scratch, need)) return rc;
+  unsigned long long* d_c = (unsigned long long*)h->rate_scratch.ptr;
+  float* d_e = (float*)((uint8_t*)h->rate_scratch.ptr + pad1k((size_t)rows * 256 * 8));
+  CK(h, cudaMemcpyAsync(d_c, counts, (size_t)rows * 256 * 8, cudaMemcpyHostToDevice, st));
+  CKL(h, launch_entropy_u64(d_c, rows, d_e, st));
+  CK(h, cudaMemcpyAsync(entropy_bits, d_e, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  return NNIC_OK;
+}
+
+// Debug aid for the parity tests: copy an intermediate activation of the most recent encode
+// (slots 0-3: conv1, conv2, conv3, conv4+res) or decode (slots 4-7: latent/255, dconv1, dconv5,
+// dconv6+res) micro-batch to host as fp32.  Returns the element count, or a negative status.
+long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity) {
+  if (!h || slot < 0 || slot > 7) return NNIC_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  const nnic_handle::Dbg& d = h->dbg[slot];
+  if (!d.count) return 0;
+  if (!out) return (long long)d.count;
+  if ((long long)d.count > capacity) return fail(h, NNIC_ERR_INVALID_ARG, "debug buffer too small");
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "sync failed");
+  if (d.f32) {
+    if (cudaMemcpy(out, d.f32, d.count * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "copy failed");
+  } else {
+    std::vector<__half> hi(d.count), lo(d.count);
+    if (cudaMemcpy(hi.data(), d.hi, d.count * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "copy failed");
+    if (cudaMemcpy(lo.data(), d.lo, d.count * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "copy failed");
+    for (size_t i = 0; i < d.count; ++i) out[i] = (__half2float(hi[i]) + __half2float(lo[i])) * ACT_INV_SCALE;
+  }
+  return (long long)d.count;
+}
+
+}  // extern "C"

@@ -1,0 +1,607 @@
+// fp32 / integer kernels of the codec path (sm_100a): colour + conv1, the generic FFMA convolution
+// used as cross-check path, dconv8 + colour inverse + uint8 pack, latent expand / quantise,
+// histogram and entropy.  Reference semantics are cited per kernel (paths relative to the
+// reference root).
+#include "kernels.h"
+
+namespace nnic {
+
+// ---------------------------------------------------------------------------------------------
+// colour constants: (float) of the reference's float64 matrices (tf2_0/src/utils.py:7-9).  The
+// inverse is np.linalg.inv(ycbcr_kernel) rounded to fp32; tests/test_host.py pins these values
+// against NumPy through nnic_colour_constants().
+// ---------------------------------------------------------------------------------------------
+static const ColourConsts g_colour = {
+    {{0x1.322d0ep-2f, 0x1.2c8b44p-1f, 0x1.d2f1aap-4f},
+     {-0x1.59945cp-3f, -0x1.5335d2p-2f, 0x1.0p-1f},
+     {0x1.0p-1f, -0x1.acbd12p-2f, -0x1.4d0bb6p-4f}},
+    {{0x1.0p+0f, -0x1.dfffacp-18f, 0x1.66e95p+0f},
+     {0x1.0p+0f, -0x1.60647p-2f, -0x1.6da38p-1f},
+     {0x1.0p+0f, 0x1.c5a1f4p+0f, 0x1.0275fap-16f}},
+    {0.0f, 0.5f, 0.5f}};
+const ColourConsts& colour_consts() { return g_colour; }
+
+struct Vec3 { float a, b, c; };
+
+// (t0*k0 + t1*k1) + t2*k2 with every op rounded separately -- utils.py:64-68 (_project); the
+// reference evaluates it as separate eager TF/NumPy ops, so no FMA contraction here.
+__device__ __forceinline__ float project(float t0, float t1, float t2, float k0, float k1, float k2) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(t0, k0), __fmul_rn(t1, k1)), __fmul_rn(t2, k2));
+}
+
+// =============================================================================================
+// conv1
+// =============================================================================================
+// Reference: Encoder.__call__ lines 39-41 (x/255, convert_to_colourspace) + BaseEncoder.conv1
+// (encoder.py:10,20): Conv2D(32, 5, 2, 'SAME', leaky_relu) on one colour plane.
+constexpr int C1_TILE = 16;                  // output tile edge
+constexpr int C1_PATCH = 2 * C1_TILE + 3;    // 35 input rows/cols
+constexpr int C1_PITCH = C1_PATCH + 1;
+
+template <int IN_KIND /*0 rgb u8, 1 f32 planes*/, bool OUT_SPLIT>
+__global__ void __launch_bounds__(256) k_conv1(const uint8_t* __restrict__ rgb, const float* __restrict__ planes,
+                                               int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+                                               const float* __restrict__ wts, const float* __restrict__ bias,
+                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                               float* __restrict__ out_f32, ColourConsts cc) {
+  __shared__ float patch[C1_PATCH * C1_PITCH];
+  __shared__ __align__(16) float w_s[25 * 32];
+  __shared__ float b_s[32];
+  const int p = blockIdx.z;
+  const int plane = p / N, n = p - plane * N;
+  const int set = plane == 0 ? 0 : 1;
+  const int tid = threadIdx.y * C1_TILE + threadIdx.x;
+  for (int i = tid; i < 25 * 32; i += 256) w_s[i] = wts[set * 25 * 32 + i];
+  if (tid < 32) b_s[tid] = bias[set * 32 + tid];
+  const int iy0 = blockIdx.y * C1_TILE * 2 - pad_t;
+  const int ix0 = blockIdx.x * C1_TILE * 2 - pad_l;
+  const float k0 = cc.k[plane][0], k1 = cc.k[plane][1], k2 = cc.k[plane][2], off = cc.off[plane];
+  for (int i = tid; i < C1_PATCH * C1_PATCH; i += 256) {
+    int r = i / C1_PATCH, c = i - r * C1_PATCH;
+    int iy = iy0 + r, ix = ix0 + c;
+    float v = 0.0f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (IN_KIND == 0) {
+        const uint8_t* px = rgb + (((size_t)n * H + iy) * W + ix) * 3;
+        // x.astype(float32)/255: IEEE division, then the projection and the offset add
+        float r_ = __fdiv_rn((float)px[0], 255.0f), g_ = __fdiv_rn((float)px[1], 255.0f),
+              b_ = __fdiv_rn((float)px[2], 255.0f);
+        v = __fadd_rn(project(r_, g_, b_, k0, k1, k2), off);
+      } else {
+        v = planes[((size_t)p * H + iy) * W + ix];
+      }
+    }
+    patch[r * C1_PITCH + c] = v;
+  }
+  __syncthreads();
+  const int oy = blockIdx.y * C1_TILE + threadIdx.y, ox = blockIdx.x * C1_TILE + threadIdx.x;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      float a = patch[(threadIdx.y * 2 + kh) * C1_PITCH + threadIdx.x * 2 + kw];
+      const float4* w4 = reinterpret_cast<const float4*>(&w_s[(kh * 5 + kw) * 32]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 w = w4[j];
+        acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+      }
+    }
+  }
+  if (oy >= Ho || ox >= Wo) return;
+  const size_t o = (((size_t)p * Ho + oy) * Wo + ox) * 32;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = leaky(__fadd_rn(acc[c], b_s[c]));
+  if (OUT_SPLIT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __align__(16) __half h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_f32(acc[8 * j + e], h[e], l[e]);
+      *reinterpret_cast<uint4*>(out_hi + o + 8 * j) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(out_lo + o + 8 * j) = *reinterpret_cast<uint4*>(l);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(out_f32 + o + 4 * j) =
+          make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  }
+}
+
+static void same_pad_host(int in, int k, int s, int& out, int& before) {
+  out = (in + s - 1) / s;
+  int tot = (out - 1) * s + k - in;
+  if (tot < 0) tot = 0;
+  before = tot / 2;
+}
+
+cudaError_t launch_conv1(const uint8_t* in_rgb, const float* in_planes, int N, int H, int W, const float* w,
+                         const float* bias, __half* out_hi, __half* out_lo, float* out_f32,
+                         cudaStream_t stream) {
+  int Ho, Wo, pt, pl;
+  same_pad_host(H, 5, 2, Ho, pt);
+  same_pad_host(W, 5, 2, Wo, pl);
+  dim3 grid((Wo + C1_TILE - 1) / C1_TILE, (Ho + C1_TILE - 1) / C1_TILE, 3 * N), block(C1_TILE, C1_TILE);
+  const ColourConsts& cc = colour_consts();
+  const bool split = out_hi != nullptr;
+  if (in_rgb) {
+    if (split) k_conv1<0, true><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, w, bias, out_hi, out_lo, nullptr, cc);
+    else k_conv1<0, false><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, w, bias, nullptr, nullptr, out_f32, cc);
+  } else {
+    if (split) k_conv1<1, true><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, w, bias, out_hi, out_lo, nullptr, cc);
+    else k_conv1<1, false><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, w, bias, nullptr, nullptr, out_f32, cc);
+  }
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// generic fp32 convolution over a tap program
+// =============================================================================================
+// Reference: Conv2D / Conv2DTranspose layers of BaseEncoder / BaseDecoder (encoder.py:10-17,
+// decoder.py:10-17) with bias, leaky_relu, the residual add (encoder.py:25, decoder.py:29) and the
+// final clip (encoder.py:32).  One block = 8x8 phase pixels x all COUT channels.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) k_simt_conv(const float* __restrict__ in, int Hi, int Wi,
+                                                   float* __restrict__ out, int Ho, int Wo, int Hp, int Wp,
+                                                   const float* __restrict__ wts, int ntaps_total,
+                                                   const float* __restrict__ bias, const float* __restrict__ res,
+                                                   const __grid_constant__ SimtJobs jobs, int n_split, int clamp01,
+                                                   int tiles_x) {
+  constexpr int NC = COUT / 4;        // channels per thread
+  constexpr int APITCH = CIN + 1;
+  __shared__ float a_s[64 * APITCH];
+  __shared__ __align__(16) float w_s[CIN * COUT];
+  const int p = blockIdx.y;
+  const int set = p < n_split ? 0 : 1;
+  const SimtJob& job = jobs.job[blockIdx.z];
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int tid = threadIdx.x;
+  const int px = tid & 63, g = tid >> 6;
+  const int Y = ty * 8 + (px >> 3), X = tx * 8 + (px & 7);
+  float acc[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
+  for (int t = 0; t < job.ntaps; ++t) {
+    const SimtTap tap = job.taps[t];
+    __syncthreads();
+    for (int i = tid; i < 64 * CIN; i += 256) {
+      int q = i / CIN, ci = i - q * CIN;
+      int iy = (ty * 8 + (q >> 3)) * jobs.in_stride + tap.dy;
+      int ix = (tx * 8 + (q & 7)) * jobs.in_stride + tap.dx;
+      float v = 0.0f;
+      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = in[(((size_t)p * Hi + iy) * Wi + ix) * CIN + ci];
+      a_s[q * APITCH + ci] = v;
+    }
+    const float* wsrc = wts + ((size_t)set * ntaps_total + tap.widx) * CIN * COUT;
+    for (int i = tid; i < CIN * COUT; i += 256) w_s[i] = wsrc[i];
+    __syncthreads();
+#pragma unroll 4
+    for (int ci = 0; ci < CIN; ++ci) {
+      float a = a_s[px * APITCH + ci];
+      const float4* w4 = reinterpret_cast<const float4*>(&w_s[ci * COUT + g * NC]);
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        float4 w = w4[j];
+        acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+      }
+    }
+  }
+  if (Y >= Hp || X >= Wp) return;
+  const int oy = Y * jobs.out_stride + job.out_oy, ox = X * jobs.out_stride + job.out_ox;
+  if (oy >= Ho || ox >= Wo) return;
+  const size_t o = (((size_t)p * Ho + oy) * Wo + ox) * COUT + g * NC;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float v = leaky(__fadd_rn(acc[j], bias[set * COUT + g * NC + j]));
+    if (res) v = __fadd_rn(v, res[o + j]);
+    if (clamp01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+    acc[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < NC / 4; ++j)
+    *reinterpret_cast<float4*>(out + o + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+}
+
+cudaError_t launch_simt_conv(int cin, int cout, const float* in, int P, int Hi, int Wi, float* out, int Ho,
+                             int Wo, int Hp, int Wp, const float* w, int ntaps_total, const float* bias,
+                             const float* res, const SimtJobs& jobs, int n_split, int clamp01,
+                             cudaStream_t stream) {
+  const int tiles_x = (Wp + 7) / 8, tiles_y = (Hp + 7) / 8;
+  dim3 grid(tiles_x * tiles_y, P, jobs.njobs), block(256);
+  if (P > 65535) return cudaErrorInvalidValue;
+#define NNIC_SIMT_CASE(CI, CO)                                                                             \
+  if (cin == CI && cout == CO) {                                                                           \
+    k_simt_conv<CI, CO><<<grid, block, 0, stream>>>(in, Hi, Wi, out, Ho, Wo, Hp, Wp, w, ntaps_total, bias, \
+                                                    res, jobs, n_split, clamp01, tiles_x);                 \
+    return cudaGetLastError();                                                                             \
+  }
+  NNIC_SIMT_CASE(32, 64)
+  NNIC_SIMT_CASE(64, 64)
+  NNIC_SIMT_CASE(64, 32)
+#undef NNIC_SIMT_CASE
+  return cudaErrorInvalidValue;
+}
+
+// =============================================================================================
+// dconv8 + colour inverse + pack
+// =============================================================================================
+// Reference: BaseDecoder.dconv8 + clip (decoder.py:17,31-32): Conv2DTranspose(1,5,2,'SAME',leaky),
+// out[2i+a-1, 2j+b-1] += x[i,j,ci]*K[a,b,0,ci]; then Decoder.__call__ lines 45-48:
+// convert_to_rgb (utils.py:70-72), clip(0,1), np.round(*255).astype(uint8).
+constexpr int D8_TILE = 16;           // output tile edge
+constexpr int D8_IN = D8_TILE / 2 + 2;  // 10 input rows/cols incl. halo
+constexpr int D8_PITCH = 68;          // floats per input pixel in smem (64 + 4: conflict-free LDS.128)
+
+template <bool SPLIT_IN>
+__global__ void __launch_bounds__(256) k_dconv8(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                const float* __restrict__ in_f32, int N, int Hi, int Wi,
+                                                const float* __restrict__ wts, const float* __restrict__ bias,
+                                                uint8_t* __restrict__ rgb, float* __restrict__ prequant,
+                                                float* __restrict__ planes_out, ColourConsts cc) {
+  __shared__ __align__(16) float in_s[D8_IN * D8_IN * D8_PITCH];
+  __shared__ __align__(16) float w_s[25 * 64];
+  __shared__ float out_s[3][D8_TILE * D8_TILE];
+  __shared__ __align__(16) uint8_t rgb_s[D8_TILE][D8_TILE * 3];
+  const int n = blockIdx.z;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Y0 = blockIdx.y * (D8_TILE / 2), X0 = blockIdx.x * (D8_TILE / 2);
+  // thread -> (output parity phase, phase pixel): a warp works on one parity so taps are uniform
+  const int ph = warp >> 1, py = ph >> 1, px = ph & 1;
+  const int idx = (warp & 1) * 32 + lane, Yl = idx >> 3, Xl = idx & 7;
+  for (int plane = 0; plane < 3; ++plane) {
+    const int p = plane * N + n;
+    const int set = plane == 0 ? 0 : 1;
+    __syncthreads();
+    for (int i = tid; i < 25 * 64; i += 256) w_s[i] = wts[set * 25 * 64 + i];
+    // input tile with a one-pixel halo, 64 channels per pixel, 4 channels per thread-iteration
+    for (int i = tid; i < D8_IN * D8_IN * 16; i += 256) {
+      int q = i >> 4, c4 = (i & 15) * 4;
+      int r = q / D8_IN, c = q - r * D8_IN;
+      int iy = Y0 + r - 1, ix = X0 + c - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
+        size_t o = (((size_t)p * Hi + iy) * Wi + ix) * 64 + c4;
+        if (SPLIT_IN) {
+          uint2 h = *reinterpret_cast<const uint2*>(in_hi + o), l = *reinterpret_cast<const uint2*>(in_lo + o);
+          const __half* hh = reinterpret_cast<const __half*>(&h);
+          const __half* ll = reinterpret_cast<const __half*>(&l);
+          v = make_float4(join_f32(hh[0], ll[0]), join_f32(hh[1], ll[1]), join_f32(hh[2], ll[2]), join_f32(hh[3], ll[3]));
+        } else {
+          v = *reinterpret_cast<const float4*>(in_f32 + o);
+        }
+      }
+      *reinterpret_cast<float4*>(&in_s[q * D8_PITCH + c4]) = v;
+    }
+    __syncthreads();
+    // taps with a = (py+1) mod 2 (+2, +4): input row = Y + (py+1-a)/2
+    float acc = 0.0f;
+    for (int a = (py + 1) & 1; a < 5; a += 2) {
+      const int r = Yl + (py + 1 - a) / 2 + 1;   // (py+1-a) is even; +1 = halo
+      for (int b = (px + 1) & 1; b < 5; b += 2) {
+        const int c = Xl + (px + 1 - b) / 2 + 1;
+        const float4* a4 = reinterpret_cast<const float4*>(&in_s[(r * D8_IN + c) * D8_PITCH]);
+        const float4* w4 = reinterpret_cast<const float4*>(&w_s[(a * 5 + b) * 64]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float4 x = a4[j], w = w4[j];
+          acc = fmaf(x.x, w.x, acc);
+          acc = fmaf(x.y, w.y, acc);
+          acc = fmaf(x.z, w.z, acc);
+          acc = fmaf(x.w, w.w, acc);
+        }
+      }
+    }
+    float v = leaky(__fadd_rn(acc, bias[set]));
+    v = fminf(fmaxf(v, 0.0f), 1.0f);                                    // decoder.py:32
+    out_s[plane][(2 * Yl + py) * D8_TILE + 2 * Xl + px] = v;
+  }
+  __syncthreads();
+  {
+    const int r = tid >> 4, c = tid & 15;
+    const int oy = blockIdx.y * D8_TILE + r, ox = blockIdx.x * D8_TILE + c;
+    const float y = out_s[0][tid], cb = out_s[1][tid], cr = out_s[2][tid];
+    const bool ok = oy < Ho && ox < Wo;
+    if (planes_out && ok) {
+      const size_t plane_sz = (size_t)N * Ho * Wo;
+      const size_t o = ((size_t)n * Ho + oy) * Wo + ox;
+      planes_out[o] = y;
+      planes_out[plane_sz + o] = cb;
+      planes_out[2 * plane_sz + o] = cr;
+    }
+    // convert_to_rgb: subtract the offsets, project with the inverse kernel, clip (decoder.py:45-46)
+    const float t0 = __fsub_rn(y, cc.off[0]), t1 = __fsub_rn(cb, cc.off[1]), t2 = __fsub_rn(cr, cc.off[2]);
+    float ch[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = project(t0, t1, t2, cc.kinv[k][0], cc.kinv[k][1], cc.kinv[k][2]);
+      ch[k] = fminf(fmaxf(v, 0.0f), 1.0f);
+    }
+    if (prequant && ok) {
+      const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * 3;
+      prequant[o] = ch[0]; prequant[o + 1] = ch[1]; prequant[o + 2] = ch[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb_s[r][c * 3 + k] = (uint8_t)rintf(__fmul_rn(ch[k], 255.0f));  // decoder.py:48
+  }
+  __syncthreads();
+  if (rgb) {
+    const int ox0 = blockIdx.x * D8_TILE;
+    const bool full_vec = (ox0 + D8_TILE <= Wo) && ((Wo * 3) % 16 == 0);
+    if (full_vec) {
+      if (tid < D8_TILE * 3) {      // 16 rows x 3 x 16-byte stores
+        const int r = tid / 3, part = tid - r * 3;
+        const int oy = blockIdx.y * D8_TILE + r;
+        if (oy < Ho) {
+          uint8_t* dst = rgb + (((size_t)n * Ho + oy) * Wo + ox0) * 3 + part * 16;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&rgb_s[r][part * 16]);
+        }
+      }
+    } else {
+      for (int i = tid; i < D8_TILE * D8_TILE * 3; i += 256) {
+        const int r = i / (D8_TILE * 3), b = i - r * (D8_TILE * 3);
+        const int oy = blockIdx.y * D8_TILE + r, ox = ox0 + b / 3;
+        if (oy < Ho && ox < Wo) rgb[(((size_t)n * Ho + oy) * Wo) * 3 + (size_t)ox0 * 3 + b] = rgb_s[r][b];
+      }
+    }
+  }
+}
+
+cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float* in_f32, int N, int Hi, int Wi,
+                          const float* w, const float* bias, uint8_t* rgb, float* prequant, float* planes,
+                          cudaStream_t stream) {
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  dim3 grid((Wo + D8_TILE - 1) / D8_TILE, (Ho + D8_TILE - 1) / D8_TILE, N), block(256);
+  if (N > 65535) return cudaErrorInvalidValue;
+  const ColourConsts& cc = colour_consts();
+  if (in_hi) k_dconv8<true><<<grid, block, 0, stream>>>(in_hi, in_lo, nullptr, N, Hi, Wi, w, bias, rgb, prequant, planes, cc);
+  else k_dconv8<false><<<grid, block, 0, stream>>>(nullptr, nullptr, in_f32, N, Hi, Wi, w, bias, rgb, prequant, planes, cc);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// latent expand / split / quantise
+// =============================================================================================
+// Reference: Decoder.__call__ lines 40-41: x.astype(float32)/255 and tf.split into 3 x 32 channels.
+template <bool OUT_SPLIT>
+__global__ void __launch_bounds__(256) k_latent_expand(const uint8_t* __restrict__ latent, int N, size_t pix,
+                                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                       float* __restrict__ out_f32) {
+  // one thread = 8 channels of one (pixel, plane); 12 threads per latent pixel
+  const size_t total = (size_t)N * pix * 12;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t gp = i / 12;              // n*pix + pixel
+    const int sub = (int)(i - gp * 12);    // 0..11 -> plane = sub/4, channel group = sub%4
+    const int plane = sub >> 2, cg = sub & 3;
+    const size_t n = gp / pix, q = gp - n * pix;
+    const uint2 raw = *reinterpret_cast<const uint2*>(latent + gp * 96 + plane * 32 + cg * 8);
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(&raw);
+    const size_t o = (((size_t)plane * N + n) * pix + q) * 32 + cg * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __fdiv_rn((float)s[e], 255.0f);
+    if (OUT_SPLIT) {
+      __align__(16) __half h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_f32(v[e], h[e], l[e]);
+      *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<uint4*>(l);
+    } else {
+      *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+static int grid_for(size_t work_items, int block) {
+  size_t g = (work_items + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+cudaError_t launch_latent_expand(const uint8_t* latent, int N, int lh, int lw, __half* out_hi, __half* out_lo,
+                                 float* out_f32, cudaStream_t stream) {
+  const size_t pix = (size_t)lh * lw;
+  const int grid = grid_for((size_t)N * pix * 12, 256);
+  if (out_hi) k_latent_expand<true><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, out_lo, nullptr);
+  else k_latent_expand<false><<<grid, 256, 0, stream>>>(latent, N, pix, nullptr, nullptr, out_f32);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_f32_to_split(const float* __restrict__ in, size_t count4,
+                                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    __align__(8) __half h[4], l[4];
+    split_f32(v.x, h[0], l[0]); split_f32(v.y, h[1], l[1]); split_f32(v.z, h[2], l[2]); split_f32(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(out_hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(out_lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+cudaError_t launch_f32_to_split(const float* in, size_t count, __half* out_hi, __half* out_lo, cudaStream_t stream) {
+  k_f32_to_split<<<grid_for(count / 4, 256), 256, 0, stream>>>(in, count / 4, out_hi, out_lo);
+  return cudaGetLastError();
+}
+
+// Reference: Encoder.__call__ lines 45,47: concat(axis=3) in plane order, np.round(e*255).astype(uint8).
+__global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ planes, int N, size_t pix,
+                                                  uint8_t* __restrict__ latent, float* __restrict__ prequant) {
+  const size_t total = (size_t)N * pix * 24;   // one thread = 4 channels of one (pixel, plane)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t gp = i / 24;
+    const int sub = (int)(i - gp * 24);
+    const int plane = sub >> 3, cg = sub & 7;
+    const size_t n = gp / pix, q = gp - n * pix;
+    const float4 v = *reinterpret_cast<const float4*>(planes + (((size_t)plane * N + n) * pix + q) * 32 + cg * 4);
+    const size_t o = gp * 96 + plane * 32 + cg * 4;
+    if (prequant) *reinterpret_cast<float4*>(prequant + o) = v;
+    uchar4 s;
+    s.x = (uint8_t)rintf(__fmul_rn(v.x, 255.0f));
+    s.y = (uint8_t)rintf(__fmul_rn(v.y, 255.0f));
+    s.z = (uint8_t)rintf(__fmul_rn(v.z, 255.0f));
+    s.w = (uint8_t)rintf(__fmul_rn(v.w, 255.0f));
+    *reinterpret_cast<uchar4*>(latent + o) = s;
+  }
+}
+cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t* latent, float* prequant,
+                            cudaStream_t stream) {
+  const size_t pix = (size_t)lh * lw;
+  k_quantise<<<grid_for((size_t)N * pix * 24, 256), 256, 0, stream>>>(planes, N, pix, latent, prequant);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// histogram + entropy
+// =============================================================================================
+// Reference: tf1_13/src/training.py:62-71.  Per (image, plane) 256-bin counts of the uint8 symbols
+// (the reference builds them with 256 equal/reduce_sum passes), p = count/numel,
+// H = sum p * (-log(clip(p,1e-5,1)) / log 2).
+//
+// One block works on a contiguous chunk of one image.  Each warp owns a private [3][256] u32
+// histogram in shared memory; symbols 0 (about half of a typical latent) never touch the atomics:
+// they are counted with a ballot/popc per plane.
+constexpr int HIST_WARPS = 8;
+constexpr int HIST_CHUNK = 96 * 256;          // bytes per block-iteration: a multiple of 96 and of 16*256
+
+__global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const uint8_t* __restrict__ latent,
+                                                          size_t bytes_per_image, int chunks_per_image,
+                                                          uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h_s[HIST_WARPS][3][256];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < HIST_WARPS * 3 * 256; i += HIST_WARPS * 32) (&h_s[0][0][0])[i] = 0;
+  __syncthreads();
+  const int n = blockIdx.x / chunks_per_image, chunk = blockIdx.x - n * chunks_per_image;
+  const uint8_t* base = latent + (size_t)n * bytes_per_image;
+  uint32_t zeros[3] = {0, 0, 0};
+  // block-stride over the image in HIST_CHUNK pieces; thread t of a piece reads bytes [16t, 16t+16)
+  for (size_t off = (size_t)chunk * HIST_CHUNK; off < bytes_per_image; off += (size_t)chunks_per_image * HIST_CHUNK) {
+#pragma unroll
+    for (int it = 0; it < HIST_CHUNK / (16 * HIST_WARPS * 32); ++it) {
+      const size_t o = off + ((size_t)it * HIST_WARPS * 32 + tid) * 16;
+      const bool ok = o < bytes_per_image;        // bytes_per_image is a multiple of 96, hence of 16
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (ok) raw = *reinterpret_cast<const uint4*>(base + o);
+      // 16 bytes never straddle a 32-channel plane group: o % 96 in {0,16,...,80}
+      const int plane = (int)((o % 96) >> 5);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t nz = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t s = (w[k] >> (8 * b)) & 0xffu;
+          if (ok && s != 0) atomicAdd(&h_s[warp][plane][s], 1u);
+          nz += (s != 0);
+        }
+      }
+      if (ok) zeros[plane] += 16 - nz;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    uint32_t z = zeros[p];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) z += __shfl_xor_sync(0xffffffffu, z, d);
+    if (lane == 0 && z) atomicAdd(&h_s[warp][p][0], z);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * 256; i += HIST_WARPS * 32) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < HIST_WARPS; ++w) s += (&h_s[w][0][0])[i];
+    if (s) atomicAdd(&hist[(size_t)n * 768 + i], s);
+  }
+}
+
+cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, cudaStream_t stream) {
+  const size_t bytes = pixels_per_image * 96;
+  // enough blocks to fill the machine a few times over, at most one per chunk
+  size_t chunks_total = (bytes + HIST_CHUNK - 1) / HIST_CHUNK;
+  size_t want = (size_t)(148 * 8 + N - 1) / N;
+  int chunks_per_image = (int)(chunks_total < want ? chunks_total : want);
+  if (chunks_per_image < 1) chunks_per_image = 1;
+  k_hist<<<(unsigned)(N * chunks_per_image), HIST_WARPS * 32, 0, stream>>>(latent, bytes, chunks_per_image, hist);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_hist_reduce(const uint32_t* __restrict__ hist, int N,
+                                                     unsigned long long* __restrict__ hist_global) {
+  const int i = blockIdx.x * 256 + threadIdx.x;   // 0..767
+  unsigned long long s = 0;
+  for (int n = 0; n < N; ++n) s += hist[(size_t)n * 768 + i];
+  hist_global[i] += s;
+}
+cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* hist_global, cudaStream_t stream) {
+  k_hist_reduce<<<3, 256, 0, stream>>>(hist, N, hist_global);
+  return cudaGetLastError();
+}
+
+// one block of 256 threads per histogram row (one thread per bin)
+template <typename CountT>
+__device__ __forceinline__ float entropy_row(const CountT* __restrict__ row, float* red) {
+  const int tid = threadIdx.x;
+  const float c = (float)row[tid];
+  red[tid] = c;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (tid < d) red[tid] += red[tid + d];   // counts are integers: exact below 2^24 per partial sum
+    __syncthreads();
+  }
+  const float numel = red[0];
+  __syncthreads();
+  const float p = numel > 0.0f ? __fdiv_rn(c, numel) : 0.0f;
+  const float pc = fminf(fmaxf(p, 1e-5f), 1.0f);
+  const float term = __fmul_rn(p, __fdiv_rn(-logf(pc), logf(2.0f)));
+  red[tid] = term;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (tid < d) red[tid] += red[tid + d];
+    __syncthreads();
+  }
+  const float h = red[0];
+  __syncthreads();
+  return h;
+}
+
+__global__ void __launch_bounds__(256) k_entropy_u32(const uint32_t* __restrict__ hist, float symbols_per_plane,
+                                                     float pixels, float* __restrict__ entropy, float* __restrict__ bpp) {
+  __shared__ float red[256];
+  const int n = blockIdx.x;
+  float e[3];
+  for (int p = 0; p < 3; ++p) e[p] = entropy_row(hist + ((size_t)n * 3 + p) * 256, red);
+  if (threadIdx.x == 0) {
+    if (entropy) { entropy[n * 3] = e[0]; entropy[n * 3 + 1] = e[1]; entropy[n * 3 + 2] = e[2]; }
+    if (bpp) {
+      float s = __fadd_rn(__fadd_rn(__fmul_rn(e[0], symbols_per_plane), __fmul_rn(e[1], symbols_per_plane)),
+                          __fmul_rn(e[2], symbols_per_plane));
+      bpp[n] = __fdiv_rn(s, pixels);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_entropy_u64(const unsigned long long* __restrict__ counts,
+                                                     float* __restrict__ entropy) {
+  __shared__ float red[256];
+  const float e = entropy_row(counts + (size_t)blockIdx.x * 256, red);
+  if (threadIdx.x == 0) entropy[blockIdx.x] = e;
+}
+cudaError_t launch_entropy_u32(const uint32_t* hist, int N, float symbols_per_plane, float pixels, float* entropy,
+                               float* bpp, cudaStream_t stream) {
+  k_entropy_u32<<<N, 256, 0, stream>>>(hist, symbols_per_plane, pixels, entropy, bpp);
+  return cudaGetLastError();
+}
+cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float* entropy, cudaStream_t stream) {
+  k_entropy_u64<<<rows, 256, 0, stream>>>(counts, entropy);
+  return cudaGetLastError();
+}
+
+}  // namespace nnic

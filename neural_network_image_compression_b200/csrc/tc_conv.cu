@@ -1,0 +1,346 @@
+// tcgen05 implicit-GEMM convolution for the eight GEMM-shaped layers of the codec
+// (conv2/3/4/8, dconv1/5/6/7 -- reference tf2_0/src/encoder.py:11-17, decoder.py:10-16).
+//
+// GEMM view per output tile:  D[128 pixels, COUT] = sum over steps  A_step[128 pixels, K] x W_step[K, COUT]
+//   * a tile is 16 rows x 8 columns of one output parity phase of one colour plane
+//   * A_step is the input activation patch of the tap (a TMA box [K, 8, 1, 16, 1] out of a 5-D view of
+//     the NHWC tensor; out-of-image pixels are zero-filled by the TMA unit = SAME padding)
+//   * operands are fp16 hi/lo pairs: D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulation in TMEM)
+//   * epilogue: 2^-k rescale, bias, leaky_relu, residual, then split-fp16 / fp32 / clamp+quantise store
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
+// warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).  Persistent: each CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; two TMEM accumulators overlap the epilogue with the MMAs.
+#include "kernels.h"
+
+namespace nnic {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kTileRows = 16, kTileCols = 8, kTileM = 128;
+constexpr uint64_t kWaitTimeoutCycles = 4000000000ull;   // ~2 s: a hung barrier traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((unsigned long long)clock64() - t0 > kWaitTimeoutCycles) {
+      if (error_flag) atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major operand tile whose rows are ROW_BYTES wide and swizzled with the matching TMA mode
+// (SWIZZLE_128B for 128-byte rows, SWIZZLE_64B for 64-byte rows); 8-row groups are dense.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = ROW_BYTES == 128 ? 2ull : 4ull;     // UMMA LayoutType: SWIZZLE_128B=2, SWIZZLE_64B=4
+  constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4;                  // stride between 8-row groups
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) /*LBO (unused for swizzled K-major)*/ |
+         (sbo << 32) | (1ull << 46) /*descriptor version: Blackwell*/ | (layout << 61);
+}
+// kind::f16, A/B fp16 K-major, D fp32, M=128, N=COUT
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int ROW_BYTES, int COUT>
+struct TcCfg {
+  static constexpr int A_BYTES = kTileM * ROW_BYTES;
+  static constexpr int W_BYTES = COUT * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int KSLAB = ROW_BYTES / 2;       // fp16 elements per A row
+  static constexpr int TMEM_COLS = 2 * COUT;        // two accumulators (64 or 128: powers of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * COUT * 4;
+};
+
+template <int ROW_BYTES, int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+          const __grid_constant__ TcLayerParams prm, int tiles_x, int tiles_y, int num_tiles, int* error_flag) {
+  using Cfg = TcCfg<ROW_BYTES, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;     // [2]
+  uint64_t* acc_empty = bars + 2 * Cfg::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [2][COUT]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+  }
+  for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) bias_s[i] = prm.bias[i];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_plane = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int job_i = t % prm.njobs;
+        int rest = t / prm.njobs;
+        const int txy = rest % tiles_per_plane;
+        const int p = rest / tiles_per_plane;
+        const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
+        const int set = p < prm.n_split ? 0 : 1;
+        const TcJob& job = prm.jobs[job_i];
+        for (int s = 0; s < job.nsteps; ++s) {
+          const TcStep st = job.steps[s];
+          mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);
+          uint8_t* sb = stage_base + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_5d(&map_a_hi, sb, &full_bar[stage], st.koff, X0 + st.dx, st.py, Y0 + st.dy, p);
+          tma_load_5d(&map_a_lo, sb + Cfg::A_BYTES, &full_bar[stage], st.koff, X0 + st.dx, st.py, Y0 + st.dy, p);
+          const int wrow = set * prm.rows_per_set + st.w_row;
+          tma_load_2d(&map_w_hi, sb + 2 * Cfg::A_BYTES, &full_bar[stage], 0, wrow);
+          tma_load_2d(&map_w_lo, sb + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &full_bar[stage], 0, wrow);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(COUT);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const TcJob& job = prm.jobs[t % prm.njobs];
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1, error_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * COUT;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < job.nsteps; ++s) {
+          const TcStep st = job.steps[s];
+          mbar_wait(&full_bar[stage], phase, error_flag, 3);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sb);
+          const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sb + Cfg::A_BYTES);
+          const uint64_t w_hi = make_smem_desc<ROW_BYTES>(sb + 2 * Cfg::A_BYTES);
+          const uint64_t w_lo = make_smem_desc<ROW_BYTES>(sb + 2 * Cfg::A_BYTES + Cfg::W_BYTES);
+          for (int ks = st.ks_begin; ks < st.ks_end; ++ks) {
+            const uint64_t koff = (uint64_t)(ks * 2);     // 16 fp16 = 32 bytes, in 16-byte descriptor units
+            umma_f16(d_tmem, a_hi + koff, w_hi + koff, idesc, accumulate);
+            accumulate = 1;
+            umma_f16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+            umma_f16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);          // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int lg = warp & 3;                  // TMEM lane group this warp may access
+    const int m = lg * 32 + lane;             // row of the tile = pixel
+    const int r = m >> 3, c = m & 7;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int job_i = t % prm.njobs;
+      int rest = t / prm.njobs;
+      const int txy = rest % tiles_per_plane;
+      const int p = rest / tiles_per_plane;
+      const int Y = (txy / tiles_x) * kTileRows + r, X = (txy % tiles_x) * kTileCols + c;
+      const int set = p < prm.n_split ? 0 : 1;
+      const TcJob& job = prm.jobs[job_i];
+      const int oy = Y * prm.out_stride + job.out_oy, ox = X * prm.out_stride + job.out_ox;
+      const bool valid = Y < prm.Hp && X < prm.Wp && oy < prm.Ho && ox < prm.Wo;
+      const float inv_scale = prm.inv_scale[set];
+      const float* bs = bias_s + set * COUT;
+      mbar_wait(&acc_full[acc], acc_phase, error_flag, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * COUT;
+      const size_t pix = ((size_t)p * prm.Ho + oy) * prm.Wo + ox;
+#pragma unroll 1
+      for (int ch = 0; ch < COUT; ch += 16) {
+        float v[16];
+        tmem_ld16(taddr + ch, v);            // warp-collective: executed by all lanes, valid or not
+        if (valid) {
+          const size_t o = pix * COUT + ch;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = leaky(__fadd_rn(v[i] * inv_scale, bs[ch + i]));
+          if (prm.res_hi) {
+            __align__(16) __half rh[16], rl[16];
+            *reinterpret_cast<uint4*>(rh) = *reinterpret_cast<const uint4*>(prm.res_hi + o);
+            *reinterpret_cast<uint4*>(rh + 8) = *reinterpret_cast<const uint4*>(prm.res_hi + o + 8);
+            *reinterpret_cast<uint4*>(rl) = *reinterpret_cast<const uint4*>(prm.res_lo + o);
+            *reinterpret_cast<uint4*>(rl + 8) = *reinterpret_cast<const uint4*>(prm.res_lo + o + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], join_f32(rh[i], rl[i]));
+          }
+          if (prm.out_mode == TC_OUT_SPLIT) {
+            __align__(16) __half h[16], l[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_f32(v[i], h[i], l[i]);
+            *reinterpret_cast<uint4*>(prm.out_hi + o) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(prm.out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 8);
+            *reinterpret_cast<uint4*>(prm.out_lo + o) = *reinterpret_cast<uint4*>(l);
+            *reinterpret_cast<uint4*>(prm.out_lo + o + 8) = *reinterpret_cast<uint4*>(l + 8);
+          } else if (prm.out_mode == TC_OUT_F32) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(prm.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            // conv8: clip(0,1) (encoder.py:32) then np.round(e*255).astype(uint8) (encoder.py:47);
+            // latent [N,Ho,Wo,96], plane-major batch p = plane*N + n, channels plane*32 + ch
+            const int N = prm.P / 3;
+            const int plane = p / N, n = p - plane * N;
+            const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + ch;
+            __align__(16) uint8_t q[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
+              q[i] = (uint8_t)rintf(__fmul_rn(v[i], 255.0f));
+            }
+            *reinterpret_cast<uint4*>(prm.out_u8 + lo_) = *reinterpret_cast<uint4*>(q);
+            if (prm.out_prequant) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(prm.out_prequant + lo_ + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
+template <int ROW_BYTES, int COUT>
+cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                        const CUtensorMap& w_lo, const TcLayerParams& prm, int num_sms, int* error_flag,
+                        cudaStream_t stream) {
+  using Cfg = TcCfg<ROW_BYTES, COUT>;
+  static bool attr_set = false;
+  auto kern = k_tc_conv<ROW_BYTES, COUT>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles_x = (prm.Wp + kTileCols - 1) / kTileCols, tiles_y = (prm.Hp + kTileRows - 1) / kTileRows;
+  const long long num_tiles_ll = (long long)tiles_x * tiles_y * prm.P * prm.njobs;
+  if (num_tiles_ll <= 0 || num_tiles_ll > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int num_tiles = (int)num_tiles_ll;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, num_tiles, error_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_tc_conv(int row_bytes, int cout, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                           const CUtensorMap& w_hi, const CUtensorMap& w_lo, const TcLayerParams& prm, int num_sms,
+                           int* error_flag, cudaStream_t stream) {
+  if (row_bytes == 128 && cout == 64) return launch_impl<128, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 128 && cout == 32) return launch_impl<128, 32>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 64 && cout == 64) return launch_impl<64, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace nnic

@@ -1,0 +1,37 @@
+"""Mirror of /root/reference/tf2_0/src/decoder.py: Decoder()(x) on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import MEM_DEVICE, MEM_HOST, _ptr
+from .utils import ProClass, _is_torch, _stream_of
+
+
+class Decoder(ProClass):
+    kind = "decoder"
+
+    def __call__(self, x, return_prequant: bool = False):
+        """decoder.py:39-48.  x: uint8 [N,h,w,96] latent -> uint8 [N,8h,8w,3] RGB (not cropped to the
+        source size, like the reference).  NumPy in -> NumPy out through host buffers; CUDA torch
+        tensor in -> CUDA tensor out, enqueued on the current stream."""
+        lib, h = self.handle.lib, self.handle.h
+        if _is_torch(x):
+            import torch
+            if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 96 or not x.is_cuda:
+                raise ValueError("expected a CUDA uint8 tensor [N,h,w,96]")
+            x = x.contiguous()
+            n, lh, lw, _ = x.shape
+            out = torch.empty((n, 8 * lh, 8 * lw, 3), dtype=torch.uint8, device=x.device)
+            pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
+            self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_DEVICE,
+                                              _stream_of(x)), "nnic_decode")
+            return (out, pre) if return_prequant else out
+        x = np.asarray(x)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[3] != 96:
+            raise ValueError("expected a uint8 array [N,h,w,96]")
+        x = np.ascontiguousarray(x)
+        n, lh, lw, _ = x.shape
+        out = np.empty((n, 8 * lh, 8 * lw, 3), np.uint8)
+        pre = np.empty(out.shape, np.float32) if return_prequant else None
+        self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_decode")
+        return (out, pre) if return_prequant else out

@@ -1,0 +1,39 @@
+"""Mirror of /root/reference/tf2_0/src/encoder.py: Encoder()(x) on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import MEM_DEVICE, MEM_HOST, _ptr
+from .utils import ProClass, _is_torch, _stream_of
+
+
+class Encoder(ProClass):
+    kind = "encoder"
+
+    def __call__(self, x, return_prequant: bool = False):
+        """encoder.py:38-47.  x: uint8 [N,H,W,3] RGB -> uint8 [N,ceil(H/8),ceil(W/8),96].
+
+        A NumPy array goes through host buffers (copied to the GPU and back inside the call, like the
+        reference's eager tensors).  A CUDA torch.uint8 tensor stays on the device: the result is a
+        CUDA tensor and the call only enqueues work on the current stream."""
+        lib, h = self.handle.lib, self.handle.h
+        if _is_torch(x):
+            import torch
+            if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3 or not x.is_cuda:
+                raise ValueError("expected a CUDA uint8 tensor [N,H,W,3]")
+            x = x.contiguous()
+            n, hh, ww, _ = x.shape
+            out = torch.empty((n, -(-hh // 8), -(-ww // 8), 96), dtype=torch.uint8, device=x.device)
+            pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
+            self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_DEVICE,
+                                              _stream_of(x)), "nnic_encode")
+            return (out, pre) if return_prequant else out
+        x = np.asarray(x)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[3] != 3:
+            raise ValueError("expected a uint8 array [N,H,W,3]")
+        x = np.ascontiguousarray(x)
+        n, hh, ww, _ = x.shape
+        out = np.empty((n, -(-hh // 8), -(-ww // 8), 96), np.uint8)
+        pre = np.empty(out.shape, np.float32) if return_prequant else None
+        self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_encode")
+        return (out, pre) if return_prequant else out
