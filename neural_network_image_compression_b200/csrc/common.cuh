@@ -39,9 +39,12 @@ struct TcStep {
   int16_t koff;        // element offset inside the view's innermost dimension
   int16_t w_row;       // first row of this step's [COUT x KSLAB] tile in the weight matrix
   int8_t ks_begin, ks_end;  // 16-element k-steps of the slab that carry non-zero weights
+  int8_t chain_end;    // 1 = the accumulation chain (one TMEM slot) ends after this step
+  int8_t pad_;
 };
 struct TcJob {
   int nsteps;
+  int nchains;         // number of accumulation chains (TMEM slots) per tile
   int out_oy, out_ox;  // output offset of this phase
   TcStep steps[MAX_STEPS];
 };

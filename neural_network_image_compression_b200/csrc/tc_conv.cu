@@ -5,12 +5,17 @@
 //   * a tile is 16 rows x 8 columns of one output parity phase of one colour plane
 //   * A_step is the input activation patch of the tap (a TMA box [K, 8, 1, 16, 1] out of a 5-D view of
 //     the NHWC tensor; out-of-image pixels are zero-filled by the TMA unit = SAME padding)
-//   * operands are fp16 hi/lo pairs: D += Ahi*Whi + Alo*Whi + Ahi*Wlo (fp32 accumulation in TMEM)
+//   * operands are fp16 hi/lo pairs: D = Ahi*Whi + (Ahi*Wlo + Alo*Whi).  The first two products are ONE
+//     MMA against the stacked B operand [Whi | Wlo] (N = 2*COUT; measured: a 128xNx16 MMA from shared memory
+//     costs max(48, N/2) cycles, so N = 128 runs at the pipe peak while three N = 64 MMAs would not)
+//   * the tensor core truncates its fp32 accumulator at every MMA (measured, tools/probe_tc.cu), so a tile is
+//     accumulated as several short chains, each in its own TMEM slot [main | correction]; the epilogue adds
+//     the chains in registers with round-to-nearest fp32 adds
 //   * epilogue: 2^-k rescale, bias, leaky_relu, residual, then split-fp16 / fp32 / clamp+quantise store
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
 // warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).  Persistent: each CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...; two TMEM accumulators overlap the epilogue with the MMAs.
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the ring of TMEM slots overlaps the epilogue with the MMAs.
 #include "kernels.h"
 
 namespace nnic {
@@ -119,7 +124,9 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int KSLAB = ROW_BYTES / 2;       // fp16 elements per A row
-  static constexpr int TMEM_COLS = 2 * COUT;        // two accumulators (64 or 128: powers of two >= 32)
+  static constexpr int SLOT_COLS = 2 * COUT;        // one accumulation chain: [main | correction] columns
+  static constexpr int SLOTS = 512 / SLOT_COLS > 8 ? 8 : 512 / SLOT_COLS;
+  static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * COUT * 4;
 };
 
@@ -133,18 +140,19 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
-  uint64_t* acc_full = bars + 2 * Cfg::STAGES;     // [2]
-  uint64_t* acc_empty = bars + 2 * Cfg::STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  uint64_t* full_bar = bars;                          // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // [STAGES]  MMA -> TMA
+  uint64_t* slot_full = bars + 2 * Cfg::STAGES;       // [SLOTS]   MMA -> epilogue
+  uint64_t* slot_empty = slot_full + Cfg::SLOTS;      // [SLOTS]   epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + Cfg::SLOTS);
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // [2][COUT]
+  static_assert((2 * Cfg::STAGES + 2 * Cfg::SLOTS) * 8 + 4 <= 256, "barrier area too small");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < Cfg::SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -189,38 +197,47 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Per k-step two MMAs:  D[slot, 0:2*COUT)    (+)= A_hi x [W_hi | W_lo]   (N = 2*COUT: hi*hi | hi*lo)
+    //                       D[slot, COUT:2*COUT)  += A_lo x  W_hi             (N = COUT:   lo*hi)
+    // so the slot's first COUT columns hold the main sum and the next COUT the correction terms.
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(COUT);
+      constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
+      constexpr uint32_t idesc_narrow = make_idesc(COUT);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+      int slot = 0; uint32_t slot_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TcJob& job = prm.jobs[t % prm.njobs];
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1, error_flag, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * COUT;
-        uint32_t accumulate = 0;
+        bool chain_start = true;
+        uint32_t d_tmem = 0;
         for (int s = 0; s < job.nsteps; ++s) {
           const TcStep st = job.steps[s];
+          if (chain_start) {
+            mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 2);
+            tc_fence_after();
+            d_tmem = tmem_base + slot * Cfg::SLOT_COLS;
+          }
           mbar_wait(&full_bar[stage], phase, error_flag, 3);
           tc_fence_after();
           const uint32_t sb = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sb);
-          const uint64_t a_lo = make_smem_desc<ROW_BYTES>(sb + Cfg::A_BYTES);
-          const uint64_t w_hi = make_smem_desc<ROW_BYTES>(sb + 2 * Cfg::A_BYTES);
-          const uint64_t w_lo = make_smem_desc<ROW_BYTES>(sb + 2 * Cfg::A_BYTES + Cfg::W_BYTES);
+          const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+          const uint64_t w_hl = a_hi + (uint64_t)((2 * Cfg::A_BYTES) >> 4);   // W_hi tile followed by the W_lo tile
+          uint32_t accumulate = chain_start ? 0u : 1u;
           for (int ks = st.ks_begin; ks < st.ks_end; ++ks) {
             const uint64_t koff = (uint64_t)(ks * 2);     // 16 fp16 = 32 bytes, in 16-byte descriptor units
-            umma_f16(d_tmem, a_hi + koff, w_hi + koff, idesc, accumulate);
-            accumulate = 1;
-            umma_f16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
-            umma_f16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+            umma_f16(d_tmem, a_hi + koff, w_hl + koff, idesc_wide, accumulate);
+            umma_f16(d_tmem + COUT, a_lo + koff, w_hl + koff, idesc_narrow, 1u);
+            accumulate = 1u;
           }
           umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          chain_start = false;
+          if (st.chain_end) {
+            umma_commit(&slot_full[slot]);    // chain complete -> epilogue
+            if (++slot == Cfg::SLOTS) { slot = 0; slot_phase ^= 1; }
+            chain_start = true;
+          }
         }
-        umma_commit(&acc_full[acc]);          // accumulator complete -> epilogue
       }
     }
   } else {
@@ -228,10 +245,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     const int lg = warp & 3;                  // TMEM lane group this warp may access
     const int m = lg * 32 + lane;             // row of the tile = pixel
     const int r = m >> 3, c = m & 7;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    int slot = 0; uint32_t slot_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int job_i = t % prm.njobs;
       int rest = t / prm.njobs;
       const int txy = rest % tiles_per_plane;
@@ -243,18 +258,35 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
       const bool valid = Y < prm.Hp && X < prm.Wp && oy < prm.Ho && ox < prm.Wo;
       const float inv_scale = prm.inv_scale[set];
       const float* bs = bias_s + set * COUT;
-      mbar_wait(&acc_full[acc], acc_phase, error_flag, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * COUT;
-      const size_t pix = ((size_t)p * prm.Ho + oy) * prm.Wo + ox;
-#pragma unroll 1
-      for (int ch = 0; ch < COUT; ch += 16) {
-        float v[16];
-        tmem_ld16(taddr + ch, v);            // warp-collective: executed by all lanes, valid or not
-        if (valid) {
-          const size_t o = pix * COUT + ch;
+      // sum the chains with round-to-nearest adds: acc += (main + correction)
+      float acc[COUT];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = leaky(__fadd_rn(v[i] * inv_scale, bs[ch + i]));
+      for (int i = 0; i < COUT; ++i) acc[i] = 0.0f;
+      for (int ch = 0; ch < job.nchains; ++ch) {
+        mbar_wait(&slot_full[slot], slot_phase, error_flag, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * Cfg::SLOT_COLS;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          float vm[16], vc[16];
+          tmem_ld16(taddr + c0, vm);
+          tmem_ld16(taddr + COUT + c0, vc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[c0 + i] = __fadd_rn(acc[c0 + i], __fadd_rn(vm[i], vc[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+        if (++slot == Cfg::SLOTS) { slot = 0; slot_phase ^= 1; }
+      }
+      if (valid) {
+        const size_t pix = ((size_t)p * prm.Ho + oy) * prm.Wo + ox;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          float* v = acc + c0;
+          const size_t o = pix * COUT + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = leaky(__fadd_rn(v[i] * inv_scale, bs[c0 + i]));
           if (prm.res_hi) {
             __align__(16) __half rh[16], rl[16];
             *reinterpret_cast<uint4*>(rh) = *reinterpret_cast<const uint4*>(prm.res_hi + o);
@@ -281,7 +313,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             // latent [N,Ho,Wo,96], plane-major batch p = plane*N + n, channels plane*32 + ch
             const int N = prm.P / 3;
             const int plane = p / N, n = p - plane * N;
-            const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + ch;
+            const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + c0;
             __align__(16) uint8_t q[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -297,9 +329,6 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
   }
 

@@ -257,15 +257,22 @@ static void probe_b() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Probe C: MMA issue rate from shared memory.  One CTA per SM; smem holds one A tile (128x64) and one B tile
-// (Nx64); a single thread issues `iters` groups of 4 k-steps and waits for the final commit.
+// Probe C: MMA rate from shared memory with a tight issue loop.  One CTA per SM; a single thread issues
+// groups of 4 k-step MMAs with descriptors precomputed in registers, then waits for the final commit.
+// mode 0: every MMA has shape 128xNx16, A tile alternates between two smem buffers
+// mode 1: the conv kernel's split pattern per k-step: 3 MMAs of N   (hi*hi, lo*hi, hi*lo)
+// mode 2: N-stacked split pattern per k-step: one MMA of 2N (A_hi x [W_hi|W_lo]) + one of N (A_lo x W_hi)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_mma_rate(int N, int iters, int distinct_a, long long* cycles_out) {
+__device__ __forceinline__ void umma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
+__global__ void __launch_bounds__(128) k_mma_rate(int N, int iters, int mode, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  for (int i = threadIdx.x * 16; i < 6 * 16384 + 32768; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x * 16; i < 4 * 16384 + 2 * 32768; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x < 32) tmem_alloc<512>(&tmem_slot);
@@ -274,15 +281,33 @@ __global__ void __launch_bounds__(128) k_mma_rate(int N, int iters, int distinct
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc(N);
+    const uint32_t idesc = make_idesc(N), idesc2 = make_idesc(2 * N);
     const uint32_t base = smem_u32(smem);
+    // A_hi(0), A_lo(1) for stage 0; A_hi(2), A_lo(3) for stage 1; W at 4*16384 (hi, then lo contiguous) per stage 32 KB
+    uint64_t a[4], w[2];
+    for (int i = 0; i < 4; ++i) a[i] = make_desc(base + i * 16384, 1024, 0);
+    for (int i = 0; i < 2; ++i) w[i] = make_desc(base + 4 * 16384 + i * 32768, 1024, 0);
+    const uint32_t w_lo_off = (uint32_t)(N * 128) >> 4;   // W_lo tile directly behind the W_hi tile
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
-      const uint32_t a_off = (uint32_t)(it % distinct_a) * 16384;
-      for (uint32_t ks = 0; ks < 4; ++ks) {
-        const uint64_t a = make_desc(base + a_off, 1024, 0) + ks * 2;
-        const uint64_t b = make_desc(base + 6 * 16384, 1024, 0) + ks * 2;
-        umma(tmem + (it & 1) * 256, a, b, idesc, 1);
+      const int st = it & 1;
+      const uint64_t ah = a[2 * st], al = a[2 * st + 1], wh = w[st];
+      if (mode == 0) {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_acc(tmem, ah + ks * 2, wh + ks * 2, idesc);
+      } else if (mode == 1) {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          umma_acc(tmem, ah + ks * 2, wh + ks * 2, idesc);
+          umma_acc(tmem, al + ks * 2, wh + ks * 2, idesc);
+          umma_acc(tmem, ah + ks * 2, wh + w_lo_off + ks * 2, idesc);
+        }
+      } else {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          umma_acc(tmem, ah + ks * 2, wh + ks * 2, idesc2);        // N-stacked [W_hi | W_lo]: 2N rows of B
+          umma_acc(tmem + 256, al + ks * 2, wh + ks * 2, idesc);
+        }
       }
     }
     umma_commit(&bar);
@@ -296,24 +321,27 @@ __global__ void __launch_bounds__(128) k_mma_rate(int N, int iters, int distinct
 }
 
 static void probe_c(int num_sms) {
-  printf("== probe C: cycles per 128xNx16 fp16 MMA issued from shared memory (SS), %d CTAs ==\n", num_sms);
+  printf("== probe C: cycles per k-step group (tight issue loop), SS operands, %d CTAs ==\n", num_sms);
   long long* d_cyc;
   CHECK(cudaMalloc(&d_cyc, num_sms * sizeof(long long)));
-  const int smem = 6 * 16384 + 32768 + 1024;
+  const int smem = 4 * 16384 + 2 * 32768 + 1024;
   CHECK(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int grid : {1, num_sms}) {
-    for (int N : {32, 64, 128, 256}) {
-      for (int distinct : {1, 6}) {
-        const int iters = 2048;
-        k_mma_rate<<<grid, 128, smem>>>(N, iters, distinct, d_cyc);
+    for (int mode = 0; mode < 3; ++mode) {
+      for (int N : {32, 64, 128, 256}) {
+        if (mode == 2 && N > 64) continue;
+        if (mode == 1 && N > 128) continue;
+        const int iters = 4096;
+        k_mma_rate<<<grid, 128, smem>>>(N, iters, mode, d_cyc);
         CHECK(cudaGetLastError());
         CHECK(cudaDeviceSynchronize());
         std::vector<long long> cyc(grid);
         CHECK(cudaMemcpy(cyc.data(), d_cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
         long long mx = 0; for (long long c : cyc) mx = c > mx ? c : mx;
-        const double per = (double)mx / (iters * 4.0);
-        printf("  grid %3d N %3d distinct-A-tiles %d: %.1f cycles per MMA  (%.0f MAC/cycle/SM; ideal %d cycles)\n", grid, N, distinct,
-               per, 128.0 * N * 16 / per, N / 2);
+        const double per = (double)mx / (iters * 4.0);      // cycles per k-step (16 K elements)
+        const double useful = mode == 0 ? 1.0 : 3.0;        // products of 128xNx16 per k-step
+        printf("  grid %3d mode %d N %3d: %.1f cycles per k-step -> %.0f MAC/cycle/SM raw (peak 4096), ideal %.0f cycles\n", grid, mode,
+               N, per, useful * 128.0 * N * 16 / per, useful * N / 2.0);
       }
     }
   }
