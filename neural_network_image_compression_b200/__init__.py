@@ -3,7 +3,7 @@
 Public surface (mirrors /root/reference/tf2_0/src): Encoder, Decoder, ProClass, plus rate().
 All arithmetic runs in libnnic.so (hand-written sm_100a CUDA); there is no CPU fallback.
 """
-from . import weights
+from . import dist, weights
 from ._lib import Handle, NnicError, colour_constants, load_library
 from .decoder import Decoder
 from .encoder import Encoder
@@ -11,4 +11,4 @@ from .rate import Rate, entropy_from_counts, rate
 from .utils import ProClass
 
 __all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "Rate", "entropy_from_counts",
-           "weights", "colour_constants", "load_library"]
+           "weights", "dist", "colour_constants", "load_library"]

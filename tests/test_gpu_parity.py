@@ -1,0 +1,259 @@
+"""GPU parity tests (run on a B200 with -m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Tolerances are BASELINE.json's: quantised symbols bit-exact except at rounding ties (mismatch fraction
+<= 1e-4, every mismatch is +-1 and lies in the documented tie band |v*255 - (k+1/2)| < 2e-3 of the fp64
+oracle), histograms bit-exact, reconstructions within 0.01 dB PSNR and 1e-3 bpp.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_weights, synthetic_images
+from oracle import nnic_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SYMBOL_MISMATCH_LIMIT = 1e-4
+TIE_BAND = 2e-3          # symbol units
+PSNR_TOL_DB = 0.01
+BPP_TOL = 1e-3
+
+
+def check_symbols(got, want, tie_dist=None, limit=SYMBOL_MISMATCH_LIMIT, min_allow=2):
+    assert got.shape == want.shape and got.dtype == np.uint8
+    diff = got != want
+    n_bad = int(diff.sum())
+    assert n_bad <= max(min_allow, limit * got.size), f"{n_bad} of {got.size} symbols differ"
+    if n_bad:
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+        if tie_dist is not None:
+            assert np.all(tie_dist[diff] < TIE_BAND), "a mismatch lies outside the rounding-tie band"
+    return n_bad
+
+
+@pytest.mark.parametrize("arith", ["tc_split", "simt_f32"])
+@pytest.mark.parametrize("wname", ["default", "spread"])
+@pytest.mark.parametrize("name", ["kodim21_crop", "imagenet_patches"])
+def test_golden_encode_rate_decode(nn, codec_factory, name, wname, arith):
+    g = load_golden(name)
+    enc, dec = codec_factory(wname, arith)
+    img = g["input"]
+    H, W = img.shape[1:3]
+    sym = enc(img)
+    check_symbols(sym, g[f"{wname}_sym64"], g[f"{wname}_tie_dist"])
+    check_symbols(sym, g[f"{wname}_sym32"])
+    # rate of the golden latent: integer histogram bit-exact, entropy / bpp to fp32 rounding
+    r = nn.rate(enc.handle, g[f"{wname}_sym64"], H, W)
+    assert np.array_equal(r.hist, g[f"{wname}_hist"])
+    assert np.array_equal(r.hist_global.astype(np.int64), g[f"{wname}_hist"].astype(np.int64).sum(axis=0))
+    assert np.abs(r.entropy_bits - g[f"{wname}_entropy"]).max() < 1e-5
+    assert np.abs(r.bpp - g[f"{wname}_bpp"]).max() < 1e-5
+    # bpp of our own latent vs the reference latent
+    assert np.abs(nn.rate(enc.handle, sym, H, W).bpp - g[f"{wname}_bpp"]).max() < BPP_TOL
+    # decode the golden latent
+    rec = dec(g[f"{wname}_sym64"])
+    check_symbols(rec, g[f"{wname}_rec64"])
+    check_symbols(rec, g[f"{wname}_rec32"])
+    for i in range(img.shape[0]):
+        assert abs(O.psnr(img[i], rec[i]) - O.psnr(img[i], g[f"{wname}_rec64"][i])) < PSNR_TOL_DB
+
+
+@pytest.mark.parametrize("wname", ["default", "spread"])
+def test_config1_kodim21_full(nn, codec_factory, wname):
+    """BASELINE.json config 1: the reference's own CPU-runnable case, one Kodak 768x512 image."""
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    img = np.array(Image.open(os.path.join(GOLDEN, "kodim21.png")))[None]
+    assert img.shape == (1, 512, 768, 3)
+    eY, eC, dY, dC = make_weights(wname)
+    enc, dec = codec_factory(wname, "tc_split")
+    sym, pre = enc(img, return_prequant=True)
+    pre64 = O.encode_prequant(img, eY, eC, "f64")
+    sym64 = O.quantise(pre64)
+    tie = np.abs(pre64 * 255.0 - np.floor(pre64 * 255.0) - 0.5)
+    check_symbols(sym, sym64, tie)
+    check_symbols(sym, O.encode(img, eY, eC, "f32"))
+    assert np.abs(pre - pre64).max() < 2e-5
+    rec = dec(sym64)
+    rec_ref = O.decode(sym64, dY, dC, "f32")
+    check_symbols(rec, rec_ref)
+    assert abs(O.psnr(img, rec) - O.psnr(img, rec_ref)) < PSNR_TOL_DB
+    r = nn.rate(enc.handle, sym, 512, 768)
+    hist, ent, bpp, _ = O.rate(sym, 512, 768)
+    assert np.array_equal(r.hist.astype(np.int64), hist)
+    assert abs(float(r.bpp[0]) - float(O.rate(sym64, 512, 768)[2][0])) < BPP_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8), (3, 8, 16), (2, 24, 40), (1, 136, 72), (5, 16, 8)])
+def test_small_and_ragged_tiles(codec_factory, shape):
+    """Smallest image, partial 16x8 tiles, batch sizes that are not multiples of anything."""
+    n, h, w = shape
+    img = synthetic_images(n, h, w, seed=h * 100 + w)
+    eY, eC, dY, dC = make_weights("spread")
+    for arith in ("tc_split", "simt_f32"):
+        enc, dec = codec_factory("spread", arith)
+        sym = enc(img)
+        assert sym.shape == (n, h // 8, w // 8, 96)
+        check_symbols(sym, O.encode(img, eY, eC, "f64"))
+        rec = dec(sym)
+        assert rec.shape == (n, h, w, 3)
+        check_symbols(rec, O.decode(sym, dY, dC, "f64"))
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 13), (2, 7, 9), (1, 1, 1), (1, 33, 50)])
+def test_sizes_not_multiple_of_8_use_ffma_path(nn, codec_factory, shape):
+    """TF SAME padding for odd sizes ((2,2) instead of (1,2)), ceil at each stride: only the FFMA arithmetic
+    accepts these; the tensor-core arithmetic refuses them loudly."""
+    n, h, w = shape
+    img = synthetic_images(n, h, w, seed=7)
+    eY, eC, dY, dC = make_weights("spread")
+    enc, dec = codec_factory("spread", "simt_f32")
+    sym = enc(img)
+    want = O.encode(img, eY, eC, "f64")
+    assert sym.shape == want.shape
+    check_symbols(sym, want)
+    rec = dec(sym)
+    check_symbols(rec, O.decode(sym, dY, dC, "f64"))
+    enc_tc, _ = codec_factory("spread", "tc_split")
+    with pytest.raises(nn.NnicError):
+        enc_tc(img)
+
+
+def test_micro_batches_and_device_api_are_equivalent(nn, codec_factory):
+    import torch
+    img = synthetic_images(7, 64, 48, seed=11)
+    enc, dec = codec_factory("spread", "tc_split")
+    ref_sym = enc(img)
+    ref_rec = dec(ref_sym)
+    for mb in (1, 2, 3):
+        enc.handle.set_micro_batch(mb); dec.handle.set_micro_batch(mb)
+        assert np.array_equal(enc(img), ref_sym)
+        assert np.array_equal(dec(ref_sym), ref_rec)
+    enc.handle.set_micro_batch(0); dec.handle.set_micro_batch(0)
+    x = torch.from_numpy(img).cuda()
+    sym_d = enc(x)
+    assert sym_d.is_cuda and np.array_equal(sym_d.cpu().numpy(), ref_sym)
+    rec_d = dec(sym_d)
+    assert np.array_equal(rec_d.cpu().numpy(), ref_rec)
+    r_d = nn.rate(enc.handle, sym_d, 64, 48)
+    r_h = nn.rate(enc.handle, ref_sym, 64, 48)
+    assert np.array_equal(r_d.hist.cpu().numpy().astype(np.uint32), r_h.hist)
+    assert np.array_equal(r_d.bpp.cpu().numpy(), r_h.bpp)
+
+
+@pytest.mark.parametrize("arith", ["tc_split", "simt_f32"])
+def test_run_model_planes(codec_factory, arith):
+    """ProClass.run_model (utils.py:19-24): float planes in, float planes out, weight sets (0,1,1)."""
+    eY, eC, dY, dC = make_weights("spread")
+    enc, dec = codec_factory("spread", arith)
+    img = synthetic_images(2, 32, 48, seed=3)
+    planes = O.rgb_to_planes(img, "f32")
+    got = enc.run_model(planes)
+    want = [O.base_encoder(planes[0], eY, "f64"), O.base_encoder(planes[1], eC, "f64"), O.base_encoder(planes[2], eC, "f64")]
+    for g_, w_ in zip(got, want):
+        assert g_.shape == w_.shape and g_.dtype == np.float32
+        assert np.abs(g_ - w_).max() < 1e-5
+    lat = [w_.astype(np.float32) for w_ in want]
+    gotd = dec.run_model(lat)
+    wantd = [O.base_decoder(lat[0], dY, "f64"), O.base_decoder(lat[1], dC, "f64"), O.base_decoder(lat[2], dC, "f64")]
+    for g_, w_ in zip(gotd, wantd):
+        assert g_.shape == w_.shape
+        assert np.abs(g_ - w_).max() < 1e-5
+
+
+def test_rate_edge_cases(nn, codec_factory):
+    enc, _ = codec_factory("default", "tc_split")
+    rng = np.random.default_rng(9)
+    cases = {
+        "zeros": np.zeros((2, 3, 5, 96), np.uint8),
+        "all255": np.full((1, 4, 4, 96), 255, np.uint8),
+        "uniform": rng.integers(0, 256, size=(3, 16, 24, 96), dtype=np.uint8),
+        "peaked": np.minimum(rng.geometric(0.3, size=(2, 64, 96, 96)) - 1, 255).astype(np.uint8),
+        "one_pixel": rng.integers(0, 256, size=(1, 1, 1, 96), dtype=np.uint8),
+    }
+    for name, lat in cases.items():
+        n, lh, lw, _ = lat.shape
+        r = nn.rate(enc.handle, lat, 8 * lh, 8 * lw)
+        hist, ent, bpp, hg = O.rate(lat, 8 * lh, 8 * lw)
+        assert np.array_equal(r.hist.astype(np.int64), hist), name
+        assert np.array_equal(r.hist_global.astype(np.int64), hg), name
+        assert int(r.hist.sum()) == lat.size
+        assert np.abs(r.entropy_bits - ent).max() < 1e-5, name
+        assert np.abs(r.bpp - bpp).max() < 1e-5, name
+    # accumulation of the global histogram over micro-batches, then entropy of the reduced counts
+    lat = cases["peaked"]
+    acc = np.zeros((3, 256), np.uint64)
+    nn.rate(enc.handle, lat[:1], hist_global=acc)
+    nn.rate(enc.handle, lat[1:], hist_global=acc)
+    want = O.histogram(lat).sum(axis=0)
+    assert np.array_equal(acc.astype(np.int64), want)
+    e = nn.entropy_from_counts(enc.handle, acc)
+    assert np.abs(e - O.entropy_from_hist(want)).max() < 1e-5
+    eg, bpp_g = nn.dist.global_rate(enc.handle, acc, 64, 96, 512, 768)
+    assert abs(bpp_g - float(O.entropy_from_hist(want).sum() * 0.5)) < 1e-4
+
+
+def test_argument_errors(nn, codec_factory):
+    enc, dec = codec_factory("default", "tc_split")
+    with pytest.raises(ValueError):
+        enc(np.zeros((1, 8, 8, 4), np.uint8))
+    with pytest.raises(ValueError):
+        enc(np.zeros((1, 8, 8, 3), np.float32))
+    with pytest.raises(ValueError):
+        dec(np.zeros((1, 2, 2, 32), np.uint8))
+    fresh = nn.Encoder(0)
+    with pytest.raises(nn.NnicError, match="not set"):
+        fresh(np.zeros((1, 8, 8, 3), np.uint8))
+    with pytest.raises(nn.NnicError):
+        nn.Handle(99)
+
+
+# ---- BASELINE.json full-size configurations: size-independent properties + cross-arithmetic check ------
+def _cross_check(nn, codec_factory, img, check_decode=True):
+    enc_tc, dec_tc = codec_factory("spread", "tc_split")
+    enc_ff, dec_ff = codec_factory("spread", "simt_f32")
+    sym = enc_tc(img)
+    sym_ff = enc_ff(img)
+    check_symbols(sym, sym_ff)
+    # batch independence: any image encoded alone gives the same bytes
+    for i in (0, img.shape[0] - 1):
+        assert np.array_equal(enc_tc(img[i:i + 1])[0], sym[i])
+    # determinism
+    assert np.array_equal(enc_tc(img), sym)
+    r = nn.rate(enc_tc.handle, sym, img.shape[1], img.shape[2])
+    assert int(r.hist.astype(np.int64).sum()) == sym.size
+    assert np.array_equal(r.hist_global.astype(np.int64), r.hist.astype(np.int64).sum(axis=0))
+    assert np.array_equal(r.hist[0, 1].astype(np.int64), np.bincount(sym[0, :, :, 32:64].ravel(), minlength=256))
+    if check_decode:
+        rec = dec_tc(sym)
+        check_symbols(rec, dec_ff(sym))
+        assert np.array_equal(dec_tc(sym[-1:])[0], rec[-1])
+    return sym
+
+
+def test_config2_kodak_batch(nn, codec_factory):
+    """24 x 768x512 full encode + rate + decode (config 2 shape)."""
+    _cross_check(nn, codec_factory, synthetic_images(24, 512, 768, seed=2))
+
+
+def test_config3_patch_batch(nn, codec_factory):
+    """ImageNet-patch shape, a 512-patch slice of the 4096 x 128x128 config: encode + rate."""
+    _cross_check(nn, codec_factory, synthetic_images(512, 128, 128, seed=3), check_decode=False)
+
+
+def test_config4_4k_decode(nn, codec_factory):
+    """3840x2160 decode-only (config 4 shape), two images."""
+    rng = np.random.default_rng(4)
+    lat = np.minimum(rng.geometric(0.08, size=(2, 270, 480, 96)) - 1, 255).astype(np.uint8)
+    _e, dec_tc = codec_factory("spread", "tc_split")
+    _e2, dec_ff = codec_factory("spread", "simt_f32")
+    rec = dec_tc(lat)
+    assert rec.shape == (2, 2160, 3840, 3)
+    check_symbols(rec, dec_ff(lat))
+    assert np.array_equal(dec_tc(lat[1:])[0], rec[1])
+
+
+def test_config5_patch_shard(nn, codec_factory):
+    """256x256 patches (config 5 shape), a 256-patch shard: encode + global histogram."""
+    sym = _cross_check(nn, codec_factory, synthetic_images(256, 256, 256, seed=5), check_decode=False)
+    assert sym.shape == (256, 32, 32, 96)

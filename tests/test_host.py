@@ -1,0 +1,105 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/nnic.h declares, the
+constants it bakes in match NumPy, the weight containers keep the Keras layouts, and nothing in the
+product imports the oracle or falls back to the CPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "neural_network_image_compression_b200")
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "nnic.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nnic_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(nn):
+    from neural_network_image_compression_b200 import _lib
+    lib = nn.load_library()
+    declared = header_functions()
+    assert len(declared) >= 18
+    bound = {name for name, _r, _a in _lib.SYMBOLS}
+    assert set(declared) == bound, (set(declared) ^ bound)
+    exported = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\sT\s{name}$", exported, flags=re.M), f"{name} not exported"
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
+    assert lib.nnic_version().startswith(b"nnic-b200")
+
+
+def test_library_is_sm100a_tensor_core_code():
+    """The shipped binary holds sm_100a SASS with tcgen05 MMA / TMEM load / TMA instructions."""
+    from neural_network_image_compression_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in out, mnemonic
+
+
+def test_colour_constants_match_reference_definition(nn):
+    """utils.py:7-9: ycbcr_kernel, np.linalg.inv(ycbcr_kernel), ycbcr_off -- rounded to fp32."""
+    k, kinv, off = nn.colour_constants()
+    K = np.array([[0.299, 0.587, 0.114], [-0.16874, -0.33126, 0.5], [0.5, -0.41869, -0.08131]])
+    assert np.array_equal(k, K.astype(np.float32))
+    assert np.array_equal(kinv, np.linalg.inv(K).astype(np.float32))
+    assert np.array_equal(off, np.array([0, 0.5, 0.5], np.float32))
+
+
+def test_weight_layouts_and_counts(nn, tmp_path):
+    Wt = nn.weights
+    enc = Wt.glorot_uniform("encoder", 1)
+    dec = Wt.glorot_uniform("decoder", 2)
+    assert enc["conv2/kernel"].shape == (5, 5, 32, 64)          # Conv2D [kh,kw,Cin,Cout]
+    assert dec["dconv1/kernel"].shape == (5, 5, 64, 32)         # Conv2DTranspose [kh,kw,Cout,Cin]
+    assert dec["dconv8/kernel"].shape == (5, 5, 1, 64)
+    n_enc = sum(v.size for v in enc.values())
+    n_dec = sum(v.size for v in dec.values())
+    assert (n_enc, n_dec) == (177184, 229185)
+    lim = np.sqrt(6.0 / ((32 + 64) * 25))
+    assert np.abs(enc["conv2/kernel"]).max() <= lim and np.all(enc["conv2/bias"] == 0)
+    Wt.check_weight_set("encoder", enc)
+    bad = dict(enc); bad["conv3/kernel"] = np.zeros((3, 3, 64, 32), np.float32)
+    with pytest.raises(ValueError):
+        Wt.check_weight_set("encoder", bad)
+    path = str(tmp_path / "encY.npz")
+    Wt.save_npz(path, enc)
+    back = Wt.load_npz(path)
+    assert all(np.array_equal(back[k], enc[k]) for k in enc)
+
+
+def test_no_cpu_fallback_without_gpu(nn):
+    """Without a GPU the product raises; it never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nn.NnicError):
+        nn.Encoder(0)
+    with pytest.raises(nn.NnicError):
+        nn.Handle(0)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _d, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text, f"{f} mentions the oracle"
+
+
+def test_shard_ranges_partition(nn):
+    sr = nn.dist.shard_range
+    for n in (0, 1, 7, 8, 65536, 65537):
+        for g in (1, 2, 3, 8):
+            rs = [sr(n, r, g) for r in range(g)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(g - 1))
+            sizes = [hi - lo for lo, hi in rs]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sr(4, 2, 2)

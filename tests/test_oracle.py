@@ -1,0 +1,117 @@
+"""CPU tests of the oracle: TensorFlow semantics pinned by an independent naive restatement, scalar
+semantics, and the committed golden vectors."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_weights
+from oracle import naive
+from oracle import nnic_oracle as O
+
+
+@pytest.mark.parametrize("hw", [(8, 12), (7, 9), (5, 5), (1, 3)])
+@pytest.mark.parametrize("ks", [(5, 2), (3, 1)])
+def test_conv_matches_naive(hw, ks):
+    rng = np.random.default_rng(1)
+    k, s = ks
+    x = rng.standard_normal((2, hw[0], hw[1], 3))
+    K = rng.standard_normal((k, k, 3, 4))
+    b = rng.standard_normal(4)
+    got = O.conv2d_same(x, K, b, s, "f64")
+    ref = naive.conv2d_same_naive(x, K, b, s)
+    assert got.shape == ref.shape == (2, -(-hw[0] // s), -(-hw[1] // s), 4)
+    assert np.abs(got - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("hw", [(8, 12), (7, 9), (1, 1)])
+@pytest.mark.parametrize("ks", [(5, 2), (3, 1)])
+def test_conv_transpose_matches_naive(hw, ks):
+    rng = np.random.default_rng(2)
+    k, s = ks
+    x = rng.standard_normal((2, hw[0], hw[1], 3))
+    K = rng.standard_normal((k, k, 4, 3))     # [kh,kw,Cout,Cin]
+    b = rng.standard_normal(4)
+    got = O.conv2d_transpose_same(x, K, b, s, "f64")
+    ref = naive.conv2d_transpose_same_naive(x, K, b, s)
+    assert got.shape == ref.shape == (2, hw[0] * s, hw[1] * s, 4)
+    assert np.abs(got - ref).max() < 1e-12
+
+
+def test_same_padding_rule():
+    # k5 s2: even sizes pad (1,2), odd sizes (2,2); k3 s1: (1,1)
+    assert O.same_pad(8, 5, 2) == (4, 1, 2)
+    assert O.same_pad(7, 5, 2) == (4, 2, 2)
+    assert O.same_pad(8, 3, 1) == (8, 1, 1)
+    assert O.same_pad(1, 5, 2) == (1, 2, 2)
+
+
+def test_scalar_semantics():
+    # true division by 255 differs from multiplying by the fp32 reciprocal for many byte values
+    v = np.arange(256, dtype=np.float32)
+    assert int(np.sum(v / np.float32(255) != v * np.float32(1 / 255))) > 100
+    # round half to even
+    assert O.quantise(np.array([0.5 / 255, 1.5 / 255, 2.5 / 255], np.float64)).tolist() == [0, 2, 2]
+    # leaky relu: alpha 0.2 on the negative side only
+    assert np.allclose(O.leaky_relu(np.array([-1.0, 2.0], np.float32)), [-0.2, 2.0])
+
+
+def test_colour_roundtrip_and_constants():
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(1, 6, 5, 3), dtype=np.uint8)
+    planes = O.rgb_to_planes(img, "f64")
+    back = O.planes_to_rgb(planes, "f64")
+    assert np.abs(back * 255 - img).max() < 1e-9
+    # fp32 flow keeps fp32 everywhere
+    assert all(p.dtype == np.float32 for p in O.rgb_to_planes(img, "f32"))
+    assert O.planes_to_rgb(O.rgb_to_planes(img, "f32"), "f32").dtype == np.float32
+    # Y row sums to 1, chroma rows to 0
+    assert abs(O.YCBCR_KERNEL[0].sum() - 1) < 1e-12 and abs(O.YCBCR_KERNEL[1].sum()) < 1e-12
+
+
+def test_histogram_entropy_definition():
+    rng = np.random.default_rng(4)
+    lat = rng.integers(0, 7, size=(2, 3, 4, 96), dtype=np.uint8)
+    lat[0, :, :, :32] = 5                      # a constant plane: one bin, entropy 0
+    hist, ent, bpp, hg = O.rate(lat, 24, 32, "f64")
+    assert hist.shape == (2, 3, 256) and hist.sum() == lat.size
+    assert hist[0, 0, 5] == 3 * 4 * 32 and ent[0, 0] == 0
+    p = hist[1, 2] / hist[1, 2].sum()
+    direct = -(p[p > 0] * np.log2(np.maximum(p[p > 0], 1e-5))).sum()
+    assert abs(ent[1, 2] - direct) < 1e-12
+    assert np.allclose(bpp, ent.sum(axis=1) * (3 * 4 * 32) / (24 * 32))
+    assert np.array_equal(hg, hist.sum(axis=0))
+    # the clip at 1e-5: a bin with probability below 1e-5 contributes p*log2(1e5), not p*log2(1/p)
+    h = np.zeros((1, 256), np.int64); h[0, 0] = 10 ** 6; h[0, 1] = 1
+    e = O.entropy_from_hist(h, "f64")[0]
+    p1 = 1 / (10 ** 6 + 1)
+    assert abs(e - (p1 * np.log2(1e5) - (1 - p1) * np.log2(1 - p1))) < 1e-12
+
+
+def test_shapes_ragged_and_empty_batch():
+    eY, eC, dY, dC = make_weights("default")
+    img = np.zeros((1, 20, 13, 3), np.uint8)           # not a multiple of 8: ceil at every stride-2 stage
+    sym = O.encode(img, eY, eC, "f32")
+    assert sym.shape == (1, 3, 2, 96) and sym.dtype == np.uint8
+    rec = O.decode(sym, dY, dC, "f32")
+    assert rec.shape == (1, 24, 16, 3)                 # 8*h, not cropped (decoder.py:39-48)
+
+
+@pytest.mark.parametrize("name", ["kodim21_crop", "imagenet_patches"])
+@pytest.mark.parametrize("wname", ["default", "spread"])
+def test_golden_vectors(name, wname):
+    g = load_golden(name)
+    eY, eC, dY, dC = make_weights(wname)
+    img = g["input"]
+    # fp64 mode reproduces the stored symbols exactly (a flip would need a value within 1e-13 of a tie)
+    sym64 = O.encode(img, eY, eC, "f64")
+    assert np.array_equal(sym64, g[f"{wname}_sym64"])
+    # fp32 mode: summation order may differ between CPUs -> only rounding ties may flip
+    sym32 = O.encode(img, eY, eC, "f32")
+    diff = sym32 != g[f"{wname}_sym64"]
+    assert diff.mean() <= 1e-4
+    assert np.abs(sym32.astype(int) - g[f"{wname}_sym64"].astype(int)).max() <= 1
+    assert np.all(g[f"{wname}_tie_dist"][diff] < 2e-3)
+    rec64 = O.decode(g[f"{wname}_sym64"], dY, dC, "f64")
+    assert np.array_equal(rec64, g[f"{wname}_rec64"])
+    hist, ent, bpp, _ = O.rate(g[f"{wname}_sym64"], img.shape[1], img.shape[2], "f32")
+    assert np.array_equal(hist, g[f"{wname}_hist"].astype(np.int64))
+    assert np.allclose(bpp, g[f"{wname}_bpp"], rtol=1e-5)
