@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the codec hot path: encode -> rate estimate -> decode, megapixels per second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl ours|reference]
+
+One process per GPU (under torchrun for N > 1; RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env).
+A step is one pass of the hot path over one synthetic batch that is already resident in HBM:
+  c2 (default, BASELINE.json configs[1]): 24 x 512x768 RGB, encode + histogram/entropy rate + decode
+  c3: 4096 x 128x128 encode + rate      c4: 16 x 2160x3840 decode only      c5: 8192 x 256x256 encode + rate
+With N GPUs every rank runs the same per-GPU batch on its own data (weak scaling: images are independent)
+and the ranks exchange one NCCL sum-allreduce of the [3,256] symbol histogram per step.
+Rank 0 prints ONE JSON line (see the field notes in DESIGN.md "Measurement").
+--impl reference times the CPU restatement of the reference (oracle/, torch-CPU fp32, all host threads) on a
+bounded sample of the same workload; TensorFlow itself cannot be installed here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (images per GPU, H, W, stages, description)
+    "c2": (24, 512, 768, ("encode", "rate", "decode"), "Kodak-shape 24x768x512 full encode+entropy estimate+decode"),
+    "c3": (4096, 128, 128, ("encode", "rate"), "ImageNet-patch 4096x128x128 encode + rate estimate"),
+    "c4": (16, 2160, 3840, ("decode",), "3840x2160 x16 decode-only"),
+    "c5": (8192, 256, 256, ("encode", "rate"), "256x256 patches, 8192 per GPU, encode + histogram allreduce"),
+}
+
+# algorithmic work per RGB pixel (3 colour planes), SURVEY.md 8a / 8d
+FLOP_PER_PX = {"conv1": 1200, "conv2": 19200, "conv3": 13824, "conv4": 13824, "conv8": 4800, "dconv1": 4800,
+               "dconv5": 13824, "dconv6": 13824, "dconv7": 38400, "dconv8": 2400}
+BYTES_PER_PX = {"conv1": 3 + 96, "dconv8": 192 + 3, "hist": 1.5, "latent_expand": 1.5 + 6, "quantise": 7.5}
+HBM_BOUND = ("conv1", "dconv8", "hist", "latent_expand", "quantise")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synthetic_batch_gpu(torch, n, h, w, seed, device):
+    """Blocky + noisy uint8 RGB batch generated on the device (natural-ish statistics)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    base = torch.randint(0, 256, (n, (h + 7) // 8, (w + 7) // 8, 3), device=device, generator=g, dtype=torch.int16)
+    up = base.repeat_interleave(8, dim=1).repeat_interleave(8, dim=2)[:, :h, :w].float()
+    noise = torch.randn((n, h, w, 3), device=device, generator=g) * 10.0
+    return (up + noise).clamp_(0, 255).to(torch.uint8)
+
+
+def synthetic_latent_gpu(torch, n, lh, lw, seed, device):
+    """uint8 latents with a peaked (geometric) symbol distribution, like an encoder output."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    u = torch.rand((n, lh, lw, 96), device=device, generator=g)
+    return (torch.log1p(-u) / -0.08).clamp_(0, 255).to(torch.uint8)
+
+
+def cpu_reference_sample(workload, n_images, threads=None):
+    """Oracle (fp32 restatement of the reference) on `n_images` of the workload; returns (MP/s, cores, text)."""
+    import numpy as np
+    import torch
+    from neural_network_image_compression_b200 import weights as Wt
+    from oracle import nnic_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    _n, H, W, stages, _d = WORKLOADS[workload]
+    rng = np.random.default_rng(0)
+    eY, eC = Wt.glorot_uniform("encoder", 11), Wt.glorot_uniform("encoder", 12)
+    dY, dC = Wt.glorot_uniform("decoder", 13), Wt.glorot_uniform("decoder", 14)
+    img = rng.integers(0, 256, size=(n_images, H, W, 3), dtype=np.uint8)
+    lat = rng.integers(0, 64, size=(n_images, H // 8, W // 8, 96), dtype=np.uint8)
+    t0 = time.perf_counter()
+    if "encode" in stages:
+        lat = O.encode(img, eY, eC, "f32")
+    if "rate" in stages:
+        O.rate(lat, H, W, "f32")
+    if "decode" in stages:
+        O.decode(lat, dY, dC, "f32")
+    dt = time.perf_counter() - t0
+    return n_images * H * W / 1e6 / dt, cores, f"{n_images} x {H}x{W} images, {'+'.join(stages)}, torch-CPU fp32 oracle"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img, H, W, stages, desc = WORKLOADS[args.workload]
+    sample = max(1, min(n_img, int(round(1.6e6 / (H * W))) or 1))      # ~1.6 MP per step: a few seconds of CPU work
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_sample(args.workload, 1)
+    vals, t0 = [], time.perf_counter()
+    text, cores = "", 0
+    for _ in range(args.steps):
+        v, cores, text = cpu_reference_sample(args.workload, sample)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    out = {"impl": "reference", "metric": "encode+decode megapixels/sec", "value": round(value, 4), "unit": "MP/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps * 1e3, 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {desc}", "sample_per_step": text},
+           "cpu_baseline": {"value": round(value, 4), "unit": "MP/s", "cores": cores, "kind": "port", "sample": text},
+           "e2e": {"value": round(value, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "CPU restatement of the reference (oracle/), not TensorFlow: TensorFlow is not installable here"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--arith", default="tc_split", choices=("tc_split", "simt_f32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-gpu-images", type=int, default=0, help="override the per-GPU batch (development)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import neural_network_image_compression_b200 as nn
+
+    rank, world, local = nn.dist.init_process_group_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_img, H, W, stages, desc = WORKLOADS[args.workload]
+    if args.per_gpu_images:
+        n_img = args.per_gpu_images
+    lh, lw = H // 8, W // 8
+    warmup = max(args.warmup, 3)
+
+    enc, dec = nn.Encoder(local, args.arith), nn.Decoder(local, args.arith)
+    enc.init_random(); dec.init_random()
+
+    # a rotating set of distinct inputs larger than the 126 MB L2 (and every step streams GBs of activations)
+    in_bytes = n_img * H * W * 3 if "encode" in stages else n_img * lh * lw * 96
+    n_sets = max(2, min(8, -(-160_000_000 // in_bytes)))
+    if "encode" in stages:
+        inputs = [synthetic_batch_gpu(torch, n_img, H, W, 1000 * rank + i, dev) for i in range(n_sets)]
+    else:
+        inputs = [synthetic_latent_gpu(torch, n_img, lh, lw, 1000 * rank + i, dev) for i in range(n_sets)]
+    lat_buf = torch.empty((n_img, lh, lw, 96), dtype=torch.uint8, device=dev)
+    rgb_buf = torch.empty((n_img, H, W, 3), dtype=torch.uint8, device=dev)
+    hist_global = torch.zeros((3, 256), dtype=torch.int64, device=dev)
+
+    def step(i):
+        x = inputs[i % n_sets]
+        lat = x
+        if "encode" in stages:
+            lat = enc(x, out=lat_buf)
+        if "rate" in stages:
+            hist_global.zero_()
+            r = nn.rate(enc.handle, lat, H, W, hist_global=hist_global)
+            nn.dist.allreduce_histogram(hist_global)        # the path's only exchange step (no-op at N=1)
+        if "decode" in stages:
+            dec(lat, out=rgb_buf)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    enc.handle.set_profiling(True); dec.handle.set_profiling(True)
+    enc.handle.profile_collect(); dec.handle.profile_collect()
+    l0 = enc.handle.launch_count + dec.handle.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = enc.handle.launch_count + dec.handle.launch_count - l0
+    prof = {}
+    for hnd in (enc.handle, dec.handle):
+        for k, (t, c) in hnd.profile_collect().items():
+            prof[k] = (prof.get(k, (0.0, 0))[0] + t, prof.get(k, (0, 0))[1] + c)
+    enc.handle.set_profiling(False); dec.handle.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    mp_per_step = world * n_img * H * W / 1e6
+    value = mp_per_step * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with pinned HOST buffers (H2D + D2H inside the timed region) ----
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.uint8, pin_memory=True).numpy()
+    h_in = pinned(tuple(inputs[0].shape)); h_in[...] = inputs[0].cpu().numpy()
+    h_lat = pinned((n_img, lh, lw, 96)); h_rgb = pinned((n_img, H, W, 3))
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        lat = h_in
+        if "encode" in stages:
+            lat = enc(h_in, out=h_lat); h2d += h_in.nbytes; d2h += h_lat.nbytes
+        if "rate" in stages:
+            r = nn.rate(enc.handle, lat, H, W); h2d += lat.nbytes; d2h += r.hist.nbytes + r.entropy_bits.nbytes + r.bpp.nbytes + 6144
+            hg = torch.from_numpy(r.hist_global.astype(np.int64)).to(dev)
+            nn.dist.allreduce_histogram(hg)
+        if "decode" in stages:
+            dec(lat, out=h_rgb); h2d += lat.nbytes; d2h += h_rgb.nbytes
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = mp_per_step * e2e_steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (event-timed inside the timed region) ----
+    peaks = measured_peaks()
+    px_per_launch = n_img * H * W          # RGB pixels one launch of a kernel covers (micro-batches: see below)
+    dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+    roofline = None
+    kernels = {}
+    for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        launches_per_step = c / args.steps
+        px = px_per_launch / launches_per_step            # pixels per launch
+        avg_ms = t / c
+        entry = {"ms_per_launch": round(avg_ms, 4), "launches_per_step": launches_per_step,
+                 "share_of_step": round(t / ms, 4)}
+        if k in HBM_BOUND and k in BYTES_PER_PX:
+            entry["GB/s"] = round(BYTES_PER_PX[k] * px / avg_ms / 1e6, 1)
+        if k in FLOP_PER_PX and k not in HBM_BOUND:
+            entry["TFLOP/s"] = round(FLOP_PER_PX[k] * px / avg_ms / 1e9, 1)
+        kernels[k] = entry
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = {}
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            traffic = json.load(f).get(args.workload, {})
+    if dom:
+        t, c = prof[dom]
+        px = px_per_launch / (c / args.steps)
+        avg_ms = t / c
+        if dom in HBM_BOUND:
+            ach = BYTES_PER_PX[dom] * px / avg_ms / 1e6
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"]}
+        else:
+            ach = FLOP_PER_PX[dom] * px / avg_ms / 1e9
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": round(ach / peaks["tflops"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"],
+                        "note": "algorithmic FLOPs; the fp16 hi/lo split issues 3x as many tensor-core FLOPs"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        sample = max(1, min(n_img, int(round(2.4e6 / (H * W))) or 1))
+        cpu_reference_sample(args.workload, 1)                      # warm-up
+        v, cores, text = cpu_reference_sample(args.workload, sample)
+        cpu_baseline = {"value": round(v, 4), "unit": "MP/s", "cores": cores, "kind": "port", "sample": text}
+
+    out = {"metric": "encode+decode megapixels/sec", "value": round(value, 2), "unit": "MP/s", "n_gpus": world,
+           "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split/f32-accumulate" if args.arith == "tc_split" else "f32",
+           "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {desc}", "images_per_gpu": n_img, "H": H, "W": W, "stages": list(stages),
+                      "weights": "random-init (Keras glorot-uniform)", "arith": args.arith,
+                      "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * in_bytes / 1e6:.0f} MB > 126 MB L2); "
+                            "each step streams > 1 GB of activations"},
+           "e2e": {"value": round(e2e_value, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "steps": e2e_steps, "api": "Encoder()(x) / rate() / Decoder()(x) on pinned NumPy buffers"},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+           "cpu_baseline": cpu_baseline}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,20 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
 int nnic_set_micro_batch(nnic_t* h, int max_images_in_flight);
 size_t nnic_scratch_bytes(const nnic_t* h);
 
+/* ---- per-kernel timing -------------------------------------------------------------------------
+ * With profiling on, every kernel launch is bracketed by CUDA events on the launching stream.
+ * nnic_profile_collect waits for them, writes the summed milliseconds and the launch count per kernel id
+ * (NNIC_KERNEL_*; arrays of at least NNIC_KERNEL_COUNT entries) since the previous collect, and returns
+ * NNIC_KERNEL_COUNT.  Used by bench.py for the roofline figures. */
+enum nnic_kernel_id {
+  NNIC_KERNEL_CONV1 = 0, NNIC_KERNEL_CONV2, NNIC_KERNEL_CONV3, NNIC_KERNEL_CONV4, NNIC_KERNEL_CONV8,
+  NNIC_KERNEL_QUANTISE, NNIC_KERNEL_EXPAND, NNIC_KERNEL_DCONV1, NNIC_KERNEL_DCONV5, NNIC_KERNEL_DCONV6,
+  NNIC_KERNEL_DCONV7, NNIC_KERNEL_DCONV8, NNIC_KERNEL_HIST, NNIC_KERNEL_ENTROPY, NNIC_KERNEL_HIST_REDUCE,
+  NNIC_KERNEL_F32_SPLIT, NNIC_KERNEL_COUNT
+};
+int nnic_set_profiling(nnic_t* h, int on);
+int nnic_profile_collect(nnic_t* h, float* ms_per_kernel, int* launches_per_kernel, int capacity);
+
 /* ---- introspection used by the parity tests ----------------------------------------------------
  * nnic_colour_constants: the fp32 colour matrices the kernels use: (float32)ycbcr_kernel,
  * (float32)np.linalg.inv(ycbcr_kernel), (float32)ycbcr_off (utils.py:7-9).  Any pointer may be NULL.

@@ -34,9 +34,15 @@ SYMBOLS = (
     ("nnic_entropy_from_counts", C.c_int, (_vp, _vp, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_set_micro_batch", C.c_int, (_vp, C.c_int)),
     ("nnic_scratch_bytes", C.c_size_t, (_vp,)),
+    ("nnic_set_profiling", C.c_int, (_vp, C.c_int)),
+    ("nnic_profile_collect", C.c_int, (_vp, _vp, _vp, C.c_int)),
     ("nnic_colour_constants", None, (_vp, _vp, _vp)),
     ("nnic_debug_fetch", C.c_longlong, (_vp, C.c_int, _vp, C.c_longlong)),
 )
+
+# include/nnic.h enum nnic_kernel_id
+KERNEL_NAMES = ("conv1", "conv2", "conv3", "conv4", "conv8", "quantise", "latent_expand", "dconv1", "dconv5",
+                "dconv6", "dconv7", "dconv8", "hist", "entropy", "hist_reduce", "f32_split")
 
 _lib = None
 
@@ -123,6 +129,18 @@ class Handle:
         k = np.ascontiguousarray(kernel, np.float32)
         b = np.ascontiguousarray(bias, np.float32)
         self.check(self.lib.nnic_set_weights(self.h, set_index, layer, _ptr(k), _ptr(b)), "nnic_set_weights")
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.nnic_set_profiling(self.h, int(bool(on))), "nnic_set_profiling")
+
+    def profile_collect(self) -> dict:
+        """{kernel name: (summed ms, launches)} since the previous collect (profiling must be on)."""
+        ms = np.zeros(len(KERNEL_NAMES), np.float32)
+        cnt = np.zeros(len(KERNEL_NAMES), np.int32)
+        rc = self.lib.nnic_profile_collect(self.h, _ptr(ms), _ptr(cnt), len(KERNEL_NAMES))
+        if rc < 0:
+            self.check(rc, "nnic_profile_collect")
+        return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(len(KERNEL_NAMES)) if cnt[i]}
 
     def debug_fetch(self, slot: int) -> np.ndarray:
         n = self.lib.nnic_debug_fetch(self.h, slot, None, 0)

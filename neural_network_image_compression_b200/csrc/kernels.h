@@ -79,6 +79,7 @@ struct TcLayerParams {
   const __half* res_hi;       // optional residual, split fp16 [P,Ho,Wo,COUT]
   const __half* res_lo;
   int out_mode;
+  int clamp01;                // clip the activation to [0,1] (conv8: encoder.py:32)
   __half* out_hi;             // TC_OUT_SPLIT
   __half* out_lo;
   float* out_f32;             // TC_OUT_F32: [P,Ho,Wo,COUT]

@@ -28,6 +28,10 @@ inline const LayerSpec& spec_of(int set, int layer) { return set < 2 ? kEnc[laye
 
 thread_local std::string g_global_error = "";
 
+// kernel ids reported by nnic_profile_collect (keep in sync with include/nnic.h NNIC_KERNEL_*)
+enum { K_CONV1 = 0, K_CONV2, K_CONV3, K_CONV4, K_CONV8, K_QUANTISE, K_EXPAND, K_DCONV1, K_DCONV5, K_DCONV6, K_DCONV7,
+       K_DCONV8, K_HIST, K_ENTROPY, K_HIST_REDUCE, K_F32_SPLIT, K_COUNT };
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -85,6 +89,13 @@ struct nnic_handle {
   size_t arena_used = 0;
   DevBuf rate_scratch;
 
+  // per-kernel CUDA-event profiling (nnic_set_profiling): one (start, stop) pair per launch
+  bool prof = false;
+  struct ProfRec { cudaEvent_t e0, e1; int id; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  int prof_id = 0;
+
   // debug: tensors of the most recent encode/decode micro-batch
   struct Dbg { const __half* hi; const __half* lo; const float* f32; size_t count; };
   Dbg dbg[8] = {};
@@ -106,10 +117,20 @@ int fail(nnic_t* h, int code, const char* fmt, ...) {
     cudaError_t e__ = (call);                                                                          \
     if (e__ != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
-#define CKL(h, call)          \
-  do {                        \
-    CK(h, call);              \
-    (h)->launches++;          \
+cudaEvent_t prof_event(nnic_t* h) {
+  if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// launch `call` (which enqueues on stream `st`) as kernel `kid`; with profiling on, bracket it with events
+#define CKL(h, kid, st, call)                                         \
+  do {                                                                \
+    cudaEvent_t pe0__ = nullptr, pe1__ = nullptr;                     \
+    if ((h)->prof) { pe0__ = prof_event(h); pe1__ = prof_event(h); cudaEventRecord(pe0__, st); } \
+    CK(h, call);                                                      \
+    if ((h)->prof) { cudaEventRecord(pe1__, st); (h)->prof_recs.push_back({pe0__, pe1__, kid}); } \
+    (h)->launches++;                                                  \
   } while (0)
 
 struct DeviceGuard {
@@ -415,7 +436,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     build_simt_jobs(sp, in.H, in.W, J);
     float* dst = out_mode == TC_OUT_F32 && out_f32_planes ? out_f32_planes : out.f32;
     const int clamp = (net == 0 && gi == 3) ? 1 : 0;
-    CKL(h, launch_simt_conv(sp.cin, sp.cout, in.f32, P, in.H, in.W, dst, Ho, Wo, Hp, Wp, h->simt[net][gi].w, sp.k * sp.k,
+    CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st, launch_simt_conv(sp.cin, sp.cout, in.f32, P, in.H, in.W, dst, Ho, Wo, Hp, Wp, h->simt[net][gi].w, sp.k * sp.k,
                             h->simt[net][gi].bias, res ? res->f32 : nullptr, J, n_split, clamp, st));
     return 0;
   }
@@ -433,10 +454,11 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
   prm.bias = L.bias;
   prm.res_hi = res ? res->hi : nullptr; prm.res_lo = res ? res->lo : nullptr;
   prm.out_mode = out_mode;
+  prm.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
   prm.out_hi = out.hi; prm.out_lo = out.lo;
   prm.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
   prm.out_u8 = out_u8; prm.out_prequant = out_prequant;
-  CKL(h, launch_tc_conv(L.row_bytes, L.cout, ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, prm, h->num_sms, h->error_flag_dev, st));
+  CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st, launch_tc_conv(L.row_bytes, L.cout, ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, prm, h->num_sms, h->error_flag_dev, st));
   return 0;
 }
 
@@ -468,7 +490,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
   Act a3 = take_act(h, split, P, H2, W2, 64);
   Act a4 = take_act(h, split, P, H2, W2, 64);
   Act a5; a5.H = H3; a5.W = W3; a5.C = 32;
-  CKL(h, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0], h->b_edge[0], a1.hi, a1.lo, a1.f32, st));
+  CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0], h->b_edge[0], a1.hi, a1.lo, a1.f32, st));
   if (int rc = run_gemm_layer(h, 0, 0, a1, a2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 1, a2, a3, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 2, a3, a4, &a2, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
@@ -484,7 +506,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
     } else {
       a5 = take_act(h, false, P, H3, W3, 32);
       if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, nullptr, st)) return rc;
-      CKL(h, launch_quantise(a5.f32, nb, H3, W3, latent, prequant, st));
+      CKL(h, K_QUANTISE, st, launch_quantise(a5.f32, nb, H3, W3, latent, prequant, st));
     }
   }
   record_dbg(h, 0, a1, P); record_dbg(h, 1, a2, P); record_dbg(h, 2, a3, P); record_dbg(h, 3, a4, P);
@@ -507,9 +529,9 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   Act d3 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
   Act d4 = take_act(h, split, P, 4 * lh, 4 * lw, 64);
   if (latent) {
-    CKL(h, launch_latent_expand(latent, nb, lh, lw, d0.hi, d0.lo, d0.f32, st));
+    CKL(h, K_EXPAND, st, launch_latent_expand(latent, nb, lh, lw, d0.hi, d0.lo, d0.f32, st));
   } else if (split) {
-    CKL(h, launch_f32_to_split(planes, (size_t)P * lh * lw * 32, d0.hi, d0.lo, st));
+    CKL(h, K_F32_SPLIT, st, launch_f32_to_split(planes, (size_t)P * lh * lw * 32, d0.hi, d0.lo, st));
   } else {
     d0.f32 = const_cast<float*>(planes);
   }
@@ -517,7 +539,7 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
-  CKL(h, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1], h->b_edge[1], rgb, prequant, out_planes, st));
+  CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1], h->b_edge[1], rgb, prequant, out_planes, st));
   record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
   h->arena_used = base_used;
   return 0;
@@ -593,6 +615,8 @@ void nnic_destroy(nnic_t* h) {
   }
   cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
   if (h->error_flag_host) cudaFreeHost(h->error_flag_host);
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -803,12 +827,12 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
     if (hist_global) d_glob = (unsigned long long*)hist_global;
   }
   CK(h, cudaMemsetAsync(d_hist, 0, hist_bytes, st));
-  CKL(h, launch_hist(d_lat, N, (size_t)lh * lw, d_hist, st));
+  CKL(h, K_HIST, st, launch_hist(d_lat, N, (size_t)lh * lw, d_hist, st));
   if (entropy_bits || bpp)
-    CKL(h, launch_entropy_u32(d_hist, N, (float)((size_t)lh * lw * 32), (float)((size_t)H * W), d_ent, d_bpp, st));
+    CKL(h, K_ENTROPY, st, launch_entropy_u32(d_hist, N, (float)((size_t)lh * lw * 32), (float)((size_t)H * W), d_ent, d_bpp, st));
   if (hist_global) {
     if (host) CK(h, cudaMemcpyAsync(d_glob, hist_global, 768 * 8, cudaMemcpyHostToDevice, st));
-    CKL(h, launch_hist_reduce(d_hist, N, d_glob, st));
+    CKL(h, K_HIST_REDUCE, st, launch_hist_reduce(d_hist, N, d_glob, st));
   }
   if (host) {
     if (hist) CK(h, cudaMemcpyAsync(hist, d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
@@ -826,7 +850,7 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (mem_kind == NNIC_MEM_DEVICE) {
-    CKL(h, launch_entropy_u64((const unsigned long long*)counts, rows, entropy_bits, st));
+    CKL(h, K_ENTROPY, st, launch_entropy_u64((const unsigned long long*)counts, rows, entropy_bits, st));
     return NNIC_OK;
   }
   size_t need = pad1k((size_t)rows * 256 * 8) + pad1k((size_t)rows * 4) + 4096;
@@ -834,10 +858,34 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
   unsigned long long* d_c = (unsigned long long*)h->rate_scratch.ptr;
   float* d_e = (float*)((uint8_t*)h->rate_scratch.ptr + pad1k((size_t)rows * 256 * 8));
   CK(h, cudaMemcpyAsync(d_c, counts, (size_t)rows * 256 * 8, cudaMemcpyHostToDevice, st));
-  CKL(h, launch_entropy_u64(d_c, rows, d_e, st));
+  CKL(h, K_ENTROPY, st, launch_entropy_u64(d_c, rows, d_e, st));
   CK(h, cudaMemcpyAsync(entropy_bits, d_e, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
   return NNIC_OK;
+}
+
+int nnic_set_profiling(nnic_t* h, int on) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  h->prof = on != 0;
+  return NNIC_OK;
+}
+
+// Sum of the event-timed durations (ms) and launch counts per kernel id since the last collect.
+int nnic_profile_collect(nnic_t* h, float* ms_per_kernel, int* launches_per_kernel, int capacity) {
+  if (!h || !ms_per_kernel || !launches_per_kernel || capacity < K_COUNT) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_profile_collect: need capacity >= %d", (int)K_COUNT);
+  DeviceGuard g(h->device);
+  for (int i = 0; i < capacity; ++i) { ms_per_kernel[i] = 0.f; launches_per_kernel[i] = 0; }
+  for (auto& r : h->prof_recs) {
+    CK(h, cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_per_kernel[r.id] += ms;
+    launches_per_kernel[r.id] += 1;
+    h->prof_pool.push_back(r.e0);
+    h->prof_pool.push_back(r.e1);
+  }
+  h->prof_recs.clear();
+  return K_COUNT;
 }
 
 // Debug aid for the parity tests: copy an intermediate activation of the most recent encode

@@ -296,6 +296,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], join_f32(rh[i], rl[i]));
           }
+          if (prm.clamp01) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
+          }
           if (prm.out_mode == TC_OUT_SPLIT) {
             __align__(16) __half h[16], l[16];
 #pragma unroll
@@ -316,10 +320,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + c0;
             __align__(16) uint8_t q[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
-              q[i] = (uint8_t)rintf(__fmul_rn(v[i], 255.0f));
-            }
+            for (int i = 0; i < 16; ++i) q[i] = (uint8_t)rintf(__fmul_rn(v[i], 255.0f));
             *reinterpret_cast<uint4*>(prm.out_u8 + lo_) = *reinterpret_cast<uint4*>(q);
             if (prm.out_prequant) {
 #pragma unroll

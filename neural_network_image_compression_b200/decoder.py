@@ -10,7 +10,7 @@ from .utils import ProClass, _is_torch, _stream_of
 class Decoder(ProClass):
     kind = "decoder"
 
-    def __call__(self, x, return_prequant: bool = False):
+    def __call__(self, x, return_prequant: bool = False, out=None):
         """decoder.py:39-48.  x: uint8 [N,h,w,96] latent -> uint8 [N,8h,8w,3] RGB (not cropped to the
         source size, like the reference).  NumPy in -> NumPy out through host buffers; CUDA torch
         tensor in -> CUDA tensor out, enqueued on the current stream."""
@@ -21,7 +21,8 @@ class Decoder(ProClass):
                 raise ValueError("expected a CUDA uint8 tensor [N,h,w,96]")
             x = x.contiguous()
             n, lh, lw, _ = x.shape
-            out = torch.empty((n, 8 * lh, 8 * lw, 3), dtype=torch.uint8, device=x.device)
+            if out is None:
+                out = torch.empty((n, 8 * lh, 8 * lw, 3), dtype=torch.uint8, device=x.device)
             pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
             self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_DEVICE,
                                               _stream_of(x)), "nnic_decode")
@@ -31,7 +32,10 @@ class Decoder(ProClass):
             raise ValueError("expected a uint8 array [N,h,w,96]")
         x = np.ascontiguousarray(x)
         n, lh, lw, _ = x.shape
-        out = np.empty((n, 8 * lh, 8 * lw, 3), np.uint8)
+        if out is None:
+            out = np.empty((n, 8 * lh, 8 * lw, 3), np.uint8)
+        elif out.shape != (n, 8 * lh, 8 * lw, 3) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape, dtype or layout")
         pre = np.empty(out.shape, np.float32) if return_prequant else None
         self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_decode")
         return (out, pre) if return_prequant else out

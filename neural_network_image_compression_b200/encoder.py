@@ -10,7 +10,7 @@ from .utils import ProClass, _is_torch, _stream_of
 class Encoder(ProClass):
     kind = "encoder"
 
-    def __call__(self, x, return_prequant: bool = False):
+    def __call__(self, x, return_prequant: bool = False, out=None):
         """encoder.py:38-47.  x: uint8 [N,H,W,3] RGB -> uint8 [N,ceil(H/8),ceil(W/8),96].
 
         A NumPy array goes through host buffers (copied to the GPU and back inside the call, like the
@@ -23,7 +23,8 @@ class Encoder(ProClass):
                 raise ValueError("expected a CUDA uint8 tensor [N,H,W,3]")
             x = x.contiguous()
             n, hh, ww, _ = x.shape
-            out = torch.empty((n, -(-hh // 8), -(-ww // 8), 96), dtype=torch.uint8, device=x.device)
+            if out is None:
+                out = torch.empty((n, -(-hh // 8), -(-ww // 8), 96), dtype=torch.uint8, device=x.device)
             pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
             self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_DEVICE,
                                               _stream_of(x)), "nnic_encode")
@@ -33,7 +34,10 @@ class Encoder(ProClass):
             raise ValueError("expected a uint8 array [N,H,W,3]")
         x = np.ascontiguousarray(x)
         n, hh, ww, _ = x.shape
-        out = np.empty((n, -(-hh // 8), -(-ww // 8), 96), np.uint8)
+        if out is None:
+            out = np.empty((n, -(-hh // 8), -(-ww // 8), 96), np.uint8)
+        elif out.shape != (n, -(-hh // 8), -(-ww // 8), 96) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape, dtype or layout")
         pre = np.empty(out.shape, np.float32) if return_prequant else None
         self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_encode")
         return (out, pre) if return_prequant else out
