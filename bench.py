@@ -128,7 +128,9 @@ def run_reference(args):
     if rank != 0:
         return
     n_img, H, W, stages, desc = WORKLOADS[args.workload]
-    sample = max(1, min(n_img, int(round(1.6e6 / (H * W))) or 1))      # ~1.6 MP per step: a few seconds of CPU work
+    sample = max(1, min(n_img, int(round(1.6e6 / (H * W))) or 1))      # ~1.6 MP per step: about a second of CPU work
+    if args.steps * sample * H * W > 64e6:                             # keep the whole run within a few minutes
+        sample = max(1, int(64e6 / (args.steps * H * W)))
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_sample(args.workload, 1)
     vals, t0 = [], time.perf_counter()

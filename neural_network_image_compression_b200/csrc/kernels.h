@@ -21,7 +21,8 @@ const ColourConsts& colour_consts();
 
 // ---- conv1: [colour +] Conv2D(1->32, 5x5, s2, SAME) + bias + leaky ----------------------------
 // in_rgb: u8 [N,H,W,3] (colour transform fused) or in_planes: f32 [3N,H,W,1].  Output [3N,Ho,Wo,32]
-// as split fp16 (out_hi/out_lo) or fp32 (out_f32).  w: [2][25][32] tap-major, bias [2][32].
+// as split fp16 (out_hi/out_lo) or fp32 (out_f32).  w: HOST [2][25][32] tap-major, bias HOST [2][32]
+// (they travel to the kernel as __grid_constant__ parameters).
 cudaError_t launch_conv1(const uint8_t* in_rgb, const float* in_planes, int N, int H, int W,
                          const float* w, const float* bias, __half* out_hi, __half* out_lo,
                          float* out_f32, cudaStream_t stream);
@@ -36,7 +37,7 @@ cudaError_t launch_simt_conv(int cin, int cout, const float* in, int P, int Hi, 
 
 // ---- dconv8: Conv2DTranspose(64->1, 5x5, s2, SAME) + bias + leaky + clip, then
 //      convert_to_rgb + clip + *255 + round + uint8 pack, all three planes of an image per block ---
-// input [3N,Hi,Wi,64] split fp16 or f32; w [2][25][64] tap-major; bias [2][1].
+// input [3N,Hi,Wi,64] split fp16 or f32; w HOST [2][25][64] tap-major; bias HOST [2][1].
 // Outputs (each optional): rgb u8 [N,2Hi,2Wi,3]; prequant f32 [N,2Hi,2Wi,3]; planes f32 [3][N,2Hi,2Wi,1].
 cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float* in_f32, int N, int Hi,
                           int Wi, const float* w, const float* bias, uint8_t* rgb, float* prequant,

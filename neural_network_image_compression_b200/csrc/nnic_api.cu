@@ -79,8 +79,8 @@ struct nnic_handle {
   bool dirty_enc = true, dirty_dec = true;
 
   // device weights: index 0 = encoder, 1 = decoder
-  float* w_edge[2] = {nullptr, nullptr};   // conv1 [2][25][32] / dconv8 [2][25][64]
-  float* b_edge[2] = {nullptr, nullptr};   // [2][32] / [2][1]
+  std::vector<float> w_edge[2];            // host: conv1 [2][25][32] / dconv8 [2][25][64] (passed as kernel parameters)
+  std::vector<float> b_edge[2];            // host: [2][32] / [2][1]
   TcLayer tc[2][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7
   SimtLayer simt[2][4];
 
@@ -304,8 +304,8 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
       memcpy(&w[s * per], h->kernel[set0 + s][l].data(), per * sizeof(float));
       memcpy(&b[s * nb], h->bias[set0 + s][l].data(), nb * sizeof(float));
     }
-    if (int rc = upload(h, (void**)&h->w_edge[net], w.data(), w.size() * 4)) return rc;
-    if (int rc = upload(h, (void**)&h->b_edge[net], b.data(), b.size() * 4)) return rc;
+    h->w_edge[net] = w;
+    h->b_edge[net] = b;
   }
   for (int gi = 0; gi < 4; ++gi) {
     const int l = net == 0 ? gi + 1 : gi;
@@ -490,7 +490,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
   Act a3 = take_act(h, split, P, H2, W2, 64);
   Act a4 = take_act(h, split, P, H2, W2, 64);
   Act a5; a5.H = H3; a5.W = W3; a5.C = 32;
-  CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0], h->b_edge[0], a1.hi, a1.lo, a1.f32, st));
+  CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0].data(), h->b_edge[0].data(), a1.hi, a1.lo, a1.f32, st));
   if (int rc = run_gemm_layer(h, 0, 0, a1, a2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 1, a2, a3, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 2, a3, a4, &a2, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
@@ -539,7 +539,7 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
-  CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1], h->b_edge[1], rgb, prequant, out_planes, st));
+  CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
   record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
   h->arena_used = base_used;
   return 0;
@@ -607,7 +607,6 @@ void nnic_destroy(nnic_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   for (int n = 0; n < 2; ++n) {
-    cudaFree(h->w_edge[n]); cudaFree(h->b_edge[n]);
     for (int i = 0; i < 4; ++i) {
       cudaFree(h->tc[n][i].w_hi); cudaFree(h->tc[n][i].w_lo); cudaFree(h->tc[n][i].bias);
       cudaFree(h->simt[n][i].w); cudaFree(h->simt[n][i].bias);

@@ -2,6 +2,8 @@
 // used as cross-check path, dconv8 + colour inverse + uint8 pack, latent expand / quantise,
 // histogram and entropy.  Reference semantics are cited per kernel (paths relative to the
 // reference root).
+#include <cstring>
+
 #include "kernels.h"
 
 namespace nnic {
@@ -34,25 +36,48 @@ __device__ __forceinline__ float project(float t0, float t1, float t2, float k0,
 // =============================================================================================
 // Reference: Encoder.__call__ lines 39-41 (x/255, convert_to_colourspace) + BaseEncoder.conv1
 // (encoder.py:10,20): Conv2D(32, 5, 2, 'SAME', leaky_relu) on one colour plane.
+// One thread = one output pixel x 32 channels.  The 25x32 weights of both networks travel as a
+// __grid_constant__ kernel parameter, so every FFMA takes its weight operand straight from the constant
+// bank (no shared-memory traffic for weights); the split-fp16 output is staged through shared memory and
+// written with fully coalesced 16-byte stores.
 constexpr int C1_TILE = 16;                  // output tile edge
 constexpr int C1_PATCH = 2 * C1_TILE + 3;    // 35 input rows/cols
 constexpr int C1_PITCH = C1_PATCH + 1;
 
+struct Conv1Weights {
+  float w[2][25][32];
+  float b[2][32];
+};
+
+template <int SET>
+__device__ __forceinline__ void conv1_accumulate(const Conv1Weights& wp, const float* patch_px, float* acc) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float a = patch_px[kh * C1_PITCH + kw];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(a, wp.w[SET][kh * 5 + kw][c], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = leaky(__fadd_rn(acc[c], wp.b[SET][c]));
+}
+
 template <int IN_KIND /*0 rgb u8, 1 f32 planes*/, bool OUT_SPLIT>
 __global__ void __launch_bounds__(256) k_conv1(const uint8_t* __restrict__ rgb, const float* __restrict__ planes,
                                                int N, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
-                                               const float* __restrict__ wts, const float* __restrict__ bias,
+                                               const __grid_constant__ Conv1Weights wp,
                                                __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                               float* __restrict__ out_f32, ColourConsts cc) {
+                                               float* __restrict__ out_f32, const __grid_constant__ ColourConsts cc) {
   __shared__ float patch[C1_PATCH * C1_PITCH];
-  __shared__ __align__(16) float w_s[25 * 32];
-  __shared__ float b_s[32];
+  __shared__ __align__(16) uint4 stage_hi[OUT_SPLIT ? 256 * 4 : 1];   // [pixel][4 x 16 B], chunk-swizzled
+  __shared__ __align__(16) uint4 stage_lo[OUT_SPLIT ? 256 * 4 : 1];
   const int p = blockIdx.z;
   const int plane = p / N, n = p - plane * N;
-  const int set = plane == 0 ? 0 : 1;
   const int tid = threadIdx.y * C1_TILE + threadIdx.x;
-  for (int i = tid; i < 25 * 32; i += 256) w_s[i] = wts[set * 25 * 32 + i];
-  if (tid < 32) b_s[tid] = bias[set * 32 + tid];
   const int iy0 = blockIdx.y * C1_TILE * 2 - pad_t;
   const int ix0 = blockIdx.x * C1_TILE * 2 - pad_l;
   const float k0 = cc.k[plane][0], k1 = cc.k[plane][1], k2 = cc.k[plane][2], off = cc.off[plane];
@@ -76,38 +101,37 @@ __global__ void __launch_bounds__(256) k_conv1(const uint8_t* __restrict__ rgb, 
   __syncthreads();
   const int oy = blockIdx.y * C1_TILE + threadIdx.y, ox = blockIdx.x * C1_TILE + threadIdx.x;
   float acc[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
-#pragma unroll
-  for (int kh = 0; kh < 5; ++kh) {
-#pragma unroll
-    for (int kw = 0; kw < 5; ++kw) {
-      float a = patch[(threadIdx.y * 2 + kh) * C1_PITCH + threadIdx.x * 2 + kw];
-      const float4* w4 = reinterpret_cast<const float4*>(&w_s[(kh * 5 + kw) * 32]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 w = w4[j];
-        acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
-        acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
-      }
-    }
-  }
-  if (oy >= Ho || ox >= Wo) return;
-  const size_t o = (((size_t)p * Ho + oy) * Wo + ox) * 32;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = leaky(__fadd_rn(acc[c], b_s[c]));
+  const float* patch_px = &patch[(threadIdx.y * 2) * C1_PITCH + threadIdx.x * 2];
+  if (plane == 0) conv1_accumulate<0>(wp, patch_px, acc);
+  else conv1_accumulate<1>(wp, patch_px, acc);
   if (OUT_SPLIT) {
+    const int sw = (tid >> 1) & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       __align__(16) __half h[8], l[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_f32(acc[8 * j + e], h[e], l[e]);
-      *reinterpret_cast<uint4*>(out_hi + o + 8 * j) = *reinterpret_cast<uint4*>(h);
-      *reinterpret_cast<uint4*>(out_lo + o + 8 * j) = *reinterpret_cast<uint4*>(l);
+      stage_hi[tid * 4 + (j ^ sw)] = *reinterpret_cast<uint4*>(h);
+      stage_lo[tid * 4 + (j ^ sw)] = *reinterpret_cast<uint4*>(l);
+    }
+    __syncthreads();
+    // chunk q = pixel*4 + j: consecutive threads write consecutive 16-byte pieces of a 1 KB tile row
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int q = it * 256 + tid;
+      const int px = q >> 2, j = q & 3;
+      const int ry = px >> 4, rx = px & 15;
+      const int y = blockIdx.y * C1_TILE + ry, x = blockIdx.x * C1_TILE + rx;
+      if (y < Ho && x < Wo) {
+        const size_t o = (((size_t)p * Ho + y) * Wo + x) * 32 + j * 8;
+        const int src = px * 4 + (j ^ ((px >> 1) & 3));
+        *reinterpret_cast<uint4*>(out_hi + o) = stage_hi[src];
+        *reinterpret_cast<uint4*>(out_lo + o) = stage_lo[src];
+      }
     }
   } else {
+    if (oy >= Ho || ox >= Wo) return;
+    const size_t o = (((size_t)p * Ho + oy) * Wo + ox) * 32;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(out_f32 + o + 4 * j) =
@@ -122,6 +146,7 @@ static void same_pad_host(int in, int k, int s, int& out, int& before) {
   before = tot / 2;
 }
 
+// w: HOST pointer to [2][25][32] tap-major weights, bias: HOST pointer to [2][32]
 cudaError_t launch_conv1(const uint8_t* in_rgb, const float* in_planes, int N, int H, int W, const float* w,
                          const float* bias, __half* out_hi, __half* out_lo, float* out_f32,
                          cudaStream_t stream) {
@@ -129,14 +154,18 @@ cudaError_t launch_conv1(const uint8_t* in_rgb, const float* in_planes, int N, i
   same_pad_host(H, 5, 2, Ho, pt);
   same_pad_host(W, 5, 2, Wo, pl);
   dim3 grid((Wo + C1_TILE - 1) / C1_TILE, (Ho + C1_TILE - 1) / C1_TILE, 3 * N), block(C1_TILE, C1_TILE);
+  if (3 * N > 65535) return cudaErrorInvalidValue;
   const ColourConsts& cc = colour_consts();
+  Conv1Weights wp;
+  memcpy(wp.w, w, sizeof wp.w);
+  memcpy(wp.b, bias, sizeof wp.b);
   const bool split = out_hi != nullptr;
   if (in_rgb) {
-    if (split) k_conv1<0, true><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, w, bias, out_hi, out_lo, nullptr, cc);
-    else k_conv1<0, false><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, w, bias, nullptr, nullptr, out_f32, cc);
+    if (split) k_conv1<0, true><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, wp, out_hi, out_lo, nullptr, cc);
+    else k_conv1<0, false><<<grid, block, 0, stream>>>(in_rgb, nullptr, N, H, W, Ho, Wo, pt, pl, wp, nullptr, nullptr, out_f32, cc);
   } else {
-    if (split) k_conv1<1, true><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, w, bias, out_hi, out_lo, nullptr, cc);
-    else k_conv1<1, false><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, w, bias, nullptr, nullptr, out_f32, cc);
+    if (split) k_conv1<1, true><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, wp, out_hi, out_lo, nullptr, cc);
+    else k_conv1<1, false><<<grid, block, 0, stream>>>(nullptr, in_planes, N, H, W, Ho, Wo, pt, pl, wp, nullptr, nullptr, out_f32, cc);
   }
   return cudaGetLastError();
 }
@@ -238,86 +267,118 @@ cudaError_t launch_simt_conv(int cin, int cout, const float* in, int P, int Hi, 
 // Reference: BaseDecoder.dconv8 + clip (decoder.py:17,31-32): Conv2DTranspose(1,5,2,'SAME',leaky),
 // out[2i+a-1, 2j+b-1] += x[i,j,ci]*K[a,b,0,ci]; then Decoder.__call__ lines 45-48:
 // convert_to_rgb (utils.py:70-72), clip(0,1), np.round(*255).astype(uint8).
-constexpr int D8_TILE = 16;           // output tile edge
-constexpr int D8_IN = D8_TILE / 2 + 2;  // 10 input rows/cols incl. halo
-constexpr int D8_PITCH = 68;          // floats per input pixel in smem (64 + 4: conflict-free LDS.128)
+//
+// One block = 14x30 input pixels (+ one pixel of halo = 16x32 = 512 positions, 4 per thread) -> 28x60 output
+// pixels of one image, all three colour planes.  Step 1: every thread computes, for its four input pixels,
+// the 25 tap responses r[a][b] = sum_ci x[ci]*K[a,b,ci]; the weights are a __grid_constant__ kernel parameter
+// read through the uniform datapath, one uniform load per four FFMAs.  Step 2: the responses go through
+// shared memory and every output pixel gathers its (at most 9) contributions in a fixed order.
+constexpr int D8_TH = 16, D8_TW = 32;                 // haloed input tile
+constexpr int D8_IH = D8_TH - 2, D8_IW = D8_TW - 2;   // interior input pixels: 14 x 30
+constexpr int D8_OH = 2 * D8_IH, D8_OW = 2 * D8_IW;   // output tile: 28 x 60
+constexpr int D8_THREADS = 128, D8_PPT = 4;           // 512 positions / 128 threads
+constexpr int D8_NPOS = D8_TH * D8_TW;
+constexpr int D8_SMEM = 25 * D8_NPOS * 4 + 3 * D8_OH * D8_OW * 4 + D8_OH * D8_OW * 3;
+
+struct Dconv8Weights {
+  float w[2][25][64];
+  float b[2];
+};
 
 template <bool SPLIT_IN>
-__global__ void __launch_bounds__(256) k_dconv8(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
-                                                const float* __restrict__ in_f32, int N, int Hi, int Wi,
-                                                const float* __restrict__ wts, const float* __restrict__ bias,
-                                                uint8_t* __restrict__ rgb, float* __restrict__ prequant,
-                                                float* __restrict__ planes_out, ColourConsts cc) {
-  __shared__ __align__(16) float in_s[D8_IN * D8_IN * D8_PITCH];
-  __shared__ __align__(16) float w_s[25 * 64];
-  __shared__ float out_s[3][D8_TILE * D8_TILE];
-  __shared__ __align__(16) uint8_t rgb_s[D8_TILE][D8_TILE * 3];
+__global__ void __launch_bounds__(D8_THREADS) k_dconv8(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                       const float* __restrict__ in_f32, int N, int Hi, int Wi,
+                                                       const __grid_constant__ Dconv8Weights wp,
+                                                       uint8_t* __restrict__ rgb, float* __restrict__ prequant,
+                                                       float* __restrict__ planes_out, const __grid_constant__ ColourConsts cc) {
+  extern __shared__ __align__(16) uint8_t d8_smem[];
+  float (*resp_s)[D8_NPOS] = reinterpret_cast<float (*)[D8_NPOS]>(d8_smem);                      // [25][512]
+  float (*out_s)[D8_OH * D8_OW] = reinterpret_cast<float (*)[D8_OH * D8_OW]>(d8_smem + 25 * D8_NPOS * 4);   // [3][1680]
+  uint8_t* rgb_s = d8_smem + 25 * D8_NPOS * 4 + 3 * D8_OH * D8_OW * 4;                           // [28][180]
   const int n = blockIdx.z;
   const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Y0 = blockIdx.y * (D8_TILE / 2), X0 = blockIdx.x * (D8_TILE / 2);
-  // thread -> (output parity phase, phase pixel): a warp works on one parity so taps are uniform
-  const int ph = warp >> 1, py = ph >> 1, px = ph & 1;
-  const int idx = (warp & 1) * 32 + lane, Yl = idx >> 3, Xl = idx & 7;
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty0 = tid >> 5;                 // position k of this thread: row ty0 + 4k, column tx
+  const int ix = blockIdx.x * D8_IW + tx - 1;
+  const int iy_base = blockIdx.y * D8_IH + ty0 - 1;
   for (int plane = 0; plane < 3; ++plane) {
     const int p = plane * N + n;
     const int set = plane == 0 ? 0 : 1;
-    __syncthreads();
-    for (int i = tid; i < 25 * 64; i += 256) w_s[i] = wts[set * 25 * 64 + i];
-    // input tile with a one-pixel halo, 64 channels per pixel, 4 channels per thread-iteration
-    for (int i = tid; i < D8_IN * D8_IN * 16; i += 256) {
-      int q = i >> 4, c4 = (i & 15) * 4;
-      int r = q / D8_IN, c = q - r * D8_IN;
-      int iy = Y0 + r - 1, ix = X0 + c - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
-        size_t o = (((size_t)p * Hi + iy) * Wi + ix) * 64 + c4;
-        if (SPLIT_IN) {
-          uint2 h = *reinterpret_cast<const uint2*>(in_hi + o), l = *reinterpret_cast<const uint2*>(in_lo + o);
-          const __half* hh = reinterpret_cast<const __half*>(&h);
-          const __half* ll = reinterpret_cast<const __half*>(&l);
-          v = make_float4(join_f32(hh[0], ll[0]), join_f32(hh[1], ll[1]), join_f32(hh[2], ll[2]), join_f32(hh[3], ll[3]));
-        } else {
-          v = *reinterpret_cast<const float4*>(in_f32 + o);
-        }
-      }
-      *reinterpret_cast<float4*>(&in_s[q * D8_PITCH + c4]) = v;
-    }
-    __syncthreads();
-    // taps with a = (py+1) mod 2 (+2, +4): input row = Y + (py+1-a)/2
-    float acc = 0.0f;
-    for (int a = (py + 1) & 1; a < 5; a += 2) {
-      const int r = Yl + (py + 1 - a) / 2 + 1;   // (py+1-a) is even; +1 = halo
-      for (int b = (px + 1) & 1; b < 5; b += 2) {
-        const int c = Xl + (px + 1 - b) / 2 + 1;
-        const float4* a4 = reinterpret_cast<const float4*>(&in_s[(r * D8_IN + c) * D8_PITCH]);
-        const float4* w4 = reinterpret_cast<const float4*>(&w_s[(a * 5 + b) * 64]);
+    float r[D8_PPT][25];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float4 x = a4[j], w = w4[j];
-          acc = fmaf(x.x, w.x, acc);
-          acc = fmaf(x.y, w.y, acc);
-          acc = fmaf(x.z, w.z, acc);
-          acc = fmaf(x.w, w.w, acc);
+    for (int k = 0; k < D8_PPT; ++k)
+#pragma unroll
+      for (int t = 0; t < 25; ++t) r[k][t] = 0.0f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      float a[D8_PPT][8];
+#pragma unroll
+      for (int k = 0; k < D8_PPT; ++k) {
+        const int iy = iy_base + 4 * k;
+        if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
+          const size_t o = (((size_t)p * Hi + iy) * Wi + ix) * 64 + c0;
+          if (SPLIT_IN) {
+            const uint4 h = *reinterpret_cast<const uint4*>(in_hi + o), l = *reinterpret_cast<const uint4*>(in_lo + o);
+            const __half* hh = reinterpret_cast<const __half*>(&h);
+            const __half* ll = reinterpret_cast<const __half*>(&l);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[k][e] = join_f32(hh[e], ll[e]);
+          } else {
+            const float4 v0 = *reinterpret_cast<const float4*>(in_f32 + o), v1 = *reinterpret_cast<const float4*>(in_f32 + o + 4);
+            a[k][0] = v0.x; a[k][1] = v0.y; a[k][2] = v0.z; a[k][3] = v0.w;
+            a[k][4] = v1.x; a[k][5] = v1.y; a[k][6] = v1.z; a[k][7] = v1.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[k][e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int t = 0; t < 25; ++t) {
+          const float w = wp.w[set][t][c0 + e];
+#pragma unroll
+          for (int k = 0; k < D8_PPT; ++k) r[k][t] = fmaf(a[k][e], w, r[k][t]);
         }
       }
     }
-    float v = leaky(__fadd_rn(acc, bias[set]));
-    v = fminf(fmaxf(v, 0.0f), 1.0f);                                    // decoder.py:32
-    out_s[plane][(2 * Yl + py) * D8_TILE + 2 * Xl + px] = v;
+    __syncthreads();                       // previous plane's gather is done with resp_s
+#pragma unroll
+    for (int k = 0; k < D8_PPT; ++k)
+#pragma unroll
+      for (int t = 0; t < 25; ++t) resp_s[t][(ty0 + 4 * k) * D8_TW + tx] = r[k][t];
+    __syncthreads();
+    const float bias = wp.b[set];
+    for (int o = tid; o < D8_OH * D8_OW; o += D8_THREADS) {
+      const int oy = o / D8_OW, ox = o - oy * D8_OW;
+      const int Y = oy >> 1, py = oy & 1, X = ox >> 1, px = ox & 1;
+      float acc = 0.0f;
+      // taps a = (py+1) mod 2 (+2, +4): input row = Y + (py+1-a)/2; +1 for the halo
+      for (int ta = (py + 1) & 1; ta < 5; ta += 2) {
+        const int rr = Y + (py + 1 - ta) / 2 + 1;
+        for (int tb = (px + 1) & 1; tb < 5; tb += 2) {
+          const int cc_ = X + (px + 1 - tb) / 2 + 1;
+          acc = __fadd_rn(acc, resp_s[ta * 5 + tb][rr * D8_TW + cc_]);
+        }
+      }
+      float v = leaky(__fadd_rn(acc, bias));
+      out_s[plane][o] = fminf(fmaxf(v, 0.0f), 1.0f);                  // decoder.py:32
+    }
   }
   __syncthreads();
-  {
-    const int r = tid >> 4, c = tid & 15;
-    const int oy = blockIdx.y * D8_TILE + r, ox = blockIdx.x * D8_TILE + c;
-    const float y = out_s[0][tid], cb = out_s[1][tid], cr = out_s[2][tid];
+  const int oy0 = blockIdx.y * D8_OH, ox0 = blockIdx.x * D8_OW;
+  for (int o = tid; o < D8_OH * D8_OW; o += D8_THREADS) {
+    const int ry = o / D8_OW, rx = o - ry * D8_OW;
+    const int oy = oy0 + ry, ox = ox0 + rx;
+    const float y = out_s[0][o], cb = out_s[1][o], cr = out_s[2][o];
     const bool ok = oy < Ho && ox < Wo;
     if (planes_out && ok) {
       const size_t plane_sz = (size_t)N * Ho * Wo;
-      const size_t o = ((size_t)n * Ho + oy) * Wo + ox;
-      planes_out[o] = y;
-      planes_out[plane_sz + o] = cb;
-      planes_out[2 * plane_sz + o] = cr;
+      const size_t q = ((size_t)n * Ho + oy) * Wo + ox;
+      planes_out[q] = y;
+      planes_out[plane_sz + q] = cb;
+      planes_out[2 * plane_sz + q] = cr;
     }
     // convert_to_rgb: subtract the offsets, project with the inverse kernel, clip (decoder.py:45-46)
     const float t0 = __fsub_rn(y, cc.off[0]), t1 = __fsub_rn(cb, cc.off[1]), t2 = __fsub_rn(cr, cc.off[2]);
@@ -328,44 +389,53 @@ __global__ void __launch_bounds__(256) k_dconv8(const __half* __restrict__ in_hi
       ch[k] = fminf(fmaxf(v, 0.0f), 1.0f);
     }
     if (prequant && ok) {
-      const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * 3;
-      prequant[o] = ch[0]; prequant[o + 1] = ch[1]; prequant[o + 2] = ch[2];
+      const size_t q = (((size_t)n * Ho + oy) * Wo + ox) * 3;
+      prequant[q] = ch[0]; prequant[q + 1] = ch[1]; prequant[q + 2] = ch[2];
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) rgb_s[r][c * 3 + k] = (uint8_t)rintf(__fmul_rn(ch[k], 255.0f));  // decoder.py:48
+    for (int k = 0; k < 3; ++k) rgb_s[ry * (D8_OW * 3) + rx * 3 + k] = (uint8_t)rintf(__fmul_rn(ch[k], 255.0f));  // decoder.py:48
   }
   __syncthreads();
   if (rgb) {
-    const int ox0 = blockIdx.x * D8_TILE;
-    const bool full_vec = (ox0 + D8_TILE <= Wo) && ((Wo * 3) % 16 == 0);
-    if (full_vec) {
-      if (tid < D8_TILE * 3) {      // 16 rows x 3 x 16-byte stores
-        const int r = tid / 3, part = tid - r * 3;
-        const int oy = blockIdx.y * D8_TILE + r;
-        if (oy < Ho) {
-          uint8_t* dst = rgb + (((size_t)n * Ho + oy) * Wo + ox0) * 3 + part * 16;
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&rgb_s[r][part * 16]);
-        }
+    constexpr int ROWB = D8_OW * 3;                              // 180 bytes per tile row, a multiple of 4
+    const bool vec4 = (ox0 + D8_OW <= Wo) && (Wo % 4 == 0);
+    if (vec4) {
+      for (int i = tid; i < D8_OH * (ROWB / 4); i += D8_THREADS) {
+        const int r_ = i / (ROWB / 4), q = i - r_ * (ROWB / 4);
+        const int oy = oy0 + r_;
+        if (oy < Ho)
+          *reinterpret_cast<uint32_t*>(rgb + (((size_t)n * Ho + oy) * Wo + ox0) * 3 + q * 4) =
+              *reinterpret_cast<const uint32_t*>(&rgb_s[r_ * ROWB + q * 4]);
       }
     } else {
-      for (int i = tid; i < D8_TILE * D8_TILE * 3; i += 256) {
-        const int r = i / (D8_TILE * 3), b = i - r * (D8_TILE * 3);
-        const int oy = blockIdx.y * D8_TILE + r, ox = ox0 + b / 3;
-        if (oy < Ho && ox < Wo) rgb[(((size_t)n * Ho + oy) * Wo) * 3 + (size_t)ox0 * 3 + b] = rgb_s[r][b];
+      for (int i = tid; i < D8_OH * ROWB; i += D8_THREADS) {
+        const int r_ = i / ROWB, b = i - r_ * ROWB;
+        const int oy = oy0 + r_, ox = ox0 + b / 3;
+        if (oy < Ho && ox < Wo) rgb[(((size_t)n * Ho + oy) * Wo) * 3 + (size_t)ox0 * 3 + b] = rgb_s[r_ * ROWB + b];
       }
     }
   }
 }
 
+// w: HOST pointer to [2][25][64] tap-major weights, bias: HOST pointer to [2][1]
 cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float* in_f32, int N, int Hi, int Wi,
                           const float* w, const float* bias, uint8_t* rgb, float* prequant, float* planes,
                           cudaStream_t stream) {
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  dim3 grid((Wo + D8_TILE - 1) / D8_TILE, (Ho + D8_TILE - 1) / D8_TILE, N), block(256);
-  if (N > 65535) return cudaErrorInvalidValue;
+  dim3 grid((Wi + D8_IW - 1) / D8_IW, (Hi + D8_IH - 1) / D8_IH, N), block(D8_THREADS);
+  if (N > 65535 || grid.y > 65535) return cudaErrorInvalidValue;
   const ColourConsts& cc = colour_consts();
-  if (in_hi) k_dconv8<true><<<grid, block, 0, stream>>>(in_hi, in_lo, nullptr, N, Hi, Wi, w, bias, rgb, prequant, planes, cc);
-  else k_dconv8<false><<<grid, block, 0, stream>>>(nullptr, nullptr, in_f32, N, Hi, Wi, w, bias, rgb, prequant, planes, cc);
+  Dconv8Weights wp;
+  memcpy(wp.w, w, sizeof wp.w);
+  wp.b[0] = bias[0]; wp.b[1] = bias[1];
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_dconv8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D8_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dconv8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D8_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (in_hi) k_dconv8<true><<<grid, block, D8_SMEM, stream>>>(in_hi, in_lo, nullptr, N, Hi, Wi, wp, rgb, prequant, planes, cc);
+  else k_dconv8<false><<<grid, block, D8_SMEM, stream>>>(nullptr, nullptr, in_f32, N, Hi, Wi, wp, rgb, prequant, planes, cc);
   return cudaGetLastError();
 }
 

@@ -102,6 +102,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of the (fully converged) warp; the same lane every time, so MMAs and their commits share a thread
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -137,7 +143,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           const __grid_constant__ TcLayerParams prm, int tiles_x, int tiles_y, int num_tiles, int* error_flag) {
   using Cfg = TcCfg<ROW_BYTES, COUT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;                          // [STAGES]  TMA -> MMA
@@ -171,19 +177,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int job_i = t % prm.njobs;
-        int rest = t / prm.njobs;
-        const int txy = rest % tiles_per_plane;
-        const int p = rest / tiles_per_plane;
-        const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
-        const int set = p < prm.n_split ? 0 : 1;
-        const TcJob& job = prm.jobs[job_i];
-        for (int s = 0; s < job.nsteps; ++s) {
-          const TcStep st = job.steps[s];
-          mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);
+    // warp-uniform control flow; one elected lane issues the copies
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int job_i = t % prm.njobs;
+      int rest = t / prm.njobs;
+      const int txy = rest % tiles_per_plane;
+      const int p = rest / tiles_per_plane;
+      const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
+      const int set = p < prm.n_split ? 0 : 1;
+      const int nsteps = prm.jobs[job_i].nsteps;
+      for (int s = 0; s < nsteps; ++s) {
+        const TcStep st = prm.jobs[job_i].steps[s];
+        mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);
+        if (elect_one()) {
           uint8_t* sb = stage_base + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_5d(&map_a_hi, sb, &full_bar[stage], st.koff, X0 + st.dx, st.py, Y0 + st.dy, p);
@@ -191,8 +198,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           const int wrow = set * prm.rows_per_set + st.w_row;
           tma_load_2d(&map_w_hi, sb + 2 * Cfg::A_BYTES, &full_bar[stage], 0, wrow);
           tma_load_2d(&map_w_lo, sb + 2 * Cfg::A_BYTES + Cfg::W_BYTES, &full_bar[stage], 0, wrow);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -200,43 +208,58 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     // Per k-step two MMAs:  D[slot, 0:2*COUT)    (+)= A_hi x [W_hi | W_lo]   (N = 2*COUT: hi*hi | hi*lo)
     //                       D[slot, COUT:2*COUT)  += A_lo x  W_hi             (N = COUT:   lo*hi)
     // so the slot's first COUT columns hold the main sum and the next COUT the correction terms.
-    if (lane == 0) {
-      constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
-      constexpr uint32_t idesc_narrow = make_idesc(COUT);
-      int stage = 0; uint32_t phase = 0;
-      int slot = 0; uint32_t slot_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TcJob& job = prm.jobs[t % prm.njobs];
-        bool chain_start = true;
-        uint32_t d_tmem = 0;
-        for (int s = 0; s < job.nsteps; ++s) {
-          const TcStep st = job.steps[s];
-          if (chain_start) {
-            mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 2);
-            tc_fence_after();
-            d_tmem = tmem_base + slot * Cfg::SLOT_COLS;
-          }
-          mbar_wait(&full_bar[stage], phase, error_flag, 3);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sb);
-          const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
-          const uint64_t w_hl = a_hi + (uint64_t)((2 * Cfg::A_BYTES) >> 4);   // W_hi tile followed by the W_lo tile
-          uint32_t accumulate = chain_start ? 0u : 1u;
-          for (int ks = st.ks_begin; ks < st.ks_end; ++ks) {
-            const uint64_t koff = (uint64_t)(ks * 2);     // 16 fp16 = 32 bytes, in 16-byte descriptor units
-            umma_f16(d_tmem, a_hi + koff, w_hl + koff, idesc_wide, accumulate);
-            umma_f16(d_tmem + COUT, a_lo + koff, w_hl + koff, idesc_narrow, 1u);
-            accumulate = 1u;
+    // Control flow is warp-uniform (all lanes wait on the barriers and compute the descriptors, which keeps
+    // them in uniform registers); one elected lane issues the MMAs and the commits.
+    constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
+    constexpr uint32_t idesc_narrow = make_idesc(COUT);
+    const uint32_t smem_base_u32 = smem_u32(stage_base);
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t slot_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int job_i = t % prm.njobs;
+      const int nsteps = prm.jobs[job_i].nsteps;
+      bool chain_start = true;
+      uint32_t d_tmem = 0;
+      for (int s = 0; s < nsteps; ++s) {
+        const int ks_begin = prm.jobs[job_i].steps[s].ks_begin, ks_end = prm.jobs[job_i].steps[s].ks_end;
+        const int chain_end = prm.jobs[job_i].steps[s].chain_end;
+        if (chain_start) {
+          mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 2);
+          d_tmem = tmem_base + slot * Cfg::SLOT_COLS;
+        }
+        mbar_wait(&full_bar[stage], phase, error_flag, 3);
+        tc_fence_after();
+        const uint32_t sb = smem_base_u32 + stage * Cfg::STAGE_BYTES;
+        const uint64_t a_hi = make_smem_desc<ROW_BYTES>(sb);
+        const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+        const uint64_t w_hl = a_hi + (uint64_t)((2 * Cfg::A_BYTES) >> 4);   // W_hi tile followed by the W_lo tile
+        if (elect_one()) {
+          if (ks_begin == 0 && ks_end == 4) {
+            umma_f16(d_tmem, a_hi, w_hl, idesc_wide, chain_start ? 0u : 1u);
+            umma_f16(d_tmem + COUT, a_lo, w_hl, idesc_narrow, 1u);
+#pragma unroll
+            for (int ks = 1; ks < 4; ++ks) {
+              umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, 1u);
+              umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+            }
+          } else {
+            uint32_t accumulate = chain_start ? 0u : 1u;
+            for (int ks = ks_begin; ks < ks_end; ++ks) {
+              const uint64_t koff = (uint64_t)(ks * 2);     // 16 fp16 = 32 bytes, in 16-byte descriptor units
+              umma_f16(d_tmem, a_hi + koff, w_hl + koff, idesc_wide, accumulate);
+              umma_f16(d_tmem + COUT, a_lo + koff, w_hl + koff, idesc_narrow, 1u);
+              accumulate = 1u;
+            }
           }
           umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs have read it
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-          chain_start = false;
-          if (st.chain_end) {
-            umma_commit(&slot_full[slot]);    // chain complete -> epilogue
-            if (++slot == Cfg::SLOTS) { slot = 0; slot_phase ^= 1; }
-            chain_start = true;
-          }
+          if (chain_end) umma_commit(&slot_full[slot]);   // chain complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        chain_start = false;
+        if (chain_end) {
+          if (++slot == Cfg::SLOTS) { slot = 0; slot_phase ^= 1; }
+          chain_start = true;
         }
       }
     }
