@@ -45,6 +45,9 @@ struct TcStep {
 struct TcJob {
   int nsteps;
   int nchains;         // number of accumulation chains (TMEM slots) per tile
+  uint32_t chain_end_mask;   // bit s = steps[s].chain_end
+  uint32_t half_mask;        // bit s = step s only uses the upper half of its slab (ks_begin = ks_end/2)
+  int ks_end;                // k-steps per full slab (4 for 128-byte rows, 2 for 64-byte rows)
   int out_oy, out_ox;  // output offset of this phase
   TcStep steps[MAX_STEPS];
 };

@@ -93,4 +93,39 @@ cudaError_t launch_tc_conv(int row_bytes, int cout, const CUtensorMap& a_hi, con
                            const CUtensorMap& w_hi, const CUtensorMap& w_lo, const TcLayerParams& prm,
                            int num_sms, int* error_flag, cudaStream_t stream);
 
+// ---- tensor-core convolution, halo-patch variant (tc_conv_patch.cu): 64 -> 64 channels, taps within the
+//      3x3 neighbourhood (conv3/4, dconv5/6, dconv7's four phases) ------------------------------------
+struct TcPatchStep {
+  uint32_t a_off;      // byte offset of the tap's first pixel row inside the hi patch (tc_patch_a_offset)
+  int16_t w_row;       // first row of this tap's [64 x 64] tile in the weight matrix
+  int16_t pad_;
+};
+struct TcPatchJob {
+  int nsteps, nchains;
+  uint32_t chain_end_mask;
+  int out_oy, out_ox;
+  TcPatchStep steps[MAX_STEPS];
+};
+struct TcPatchParams {
+  int njobs;
+  TcPatchJob jobs[MAX_JOBS];
+  int P, n_split;
+  int Hp, Wp;
+  int Ho, Wo, out_stride;
+  int rows_per_set;
+  float inv_scale[2];
+  const float* bias;
+  const __half* res_hi;
+  const __half* res_lo;
+  int out_mode;               // TC_OUT_SPLIT or TC_OUT_F32
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+};
+uint32_t tc_patch_a_offset(int dy, int dx);
+// a_hi / a_lo: plain activation views with box [64, 10, 1, 18, 1]
+cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                 const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
+                                 cudaStream_t stream);
+
 }  // namespace nnic

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ struct TcLayer {
   float* bias = nullptr;       // [2][cout]
   CUtensorMap map_w_hi, map_w_lo;
   bool parity_view = false;    // input read through the [2C, W/2, 2, H/2, P] view (stride-2 convs)
+  bool use_patch = false;      // all taps within the 3x3 neighbourhood, 64 -> 64: halo-patch kernel
   int out_stride = 1;
 };
 struct SimtLayer {
@@ -69,6 +71,7 @@ struct nnic_handle {
   std::string err;
   uint64_t launches = 0;
   int micro_batch = 0;
+  bool tc_patch = true;             // use the halo-patch kernel where it applies (NNIC_TC_PATCH=0 disables)
   EncodeTiledFn encode_tiled = nullptr;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
   int* error_flag_dev = nullptr;
@@ -174,7 +177,7 @@ int make_map(nnic_t* h, CUtensorMap* map, void* base, int rank, const cuuint64_t
 }
 // activation view [inner, X, PY, Y, P] of a split-fp16 tensor [P,H,W,C]
 int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, int W, int C, bool parity, int kslab,
-                 int row_bytes) {
+                 int row_bytes, int box_cols = 8, int box_rows = 16) {
   cuuint64_t dims[5], strides[4];
   if (!parity) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = P;
@@ -185,7 +188,7 @@ int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, 
     strides[0] = (cuuint64_t)2 * C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)2 * W * C * 2;
     strides[3] = (cuuint64_t)H * W * C * 2;
   }
-  cuuint32_t box[5] = {(cuuint32_t)kslab, 8, 1, 16, 1};
+  cuuint32_t box[5] = {(cuuint32_t)kslab, (cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};
   return make_map(h, map, const_cast<__half*>(base), 5, dims, strides, box, row_bytes);
 }
 
@@ -247,6 +250,7 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     }
     L.rows_per_set = 25 * sp.cout;
   }
+  L.use_patch = sp.cin == 64 && sp.cout == 64 && !(L.parity_view);
   // Accumulation chains: the tensor core truncates its fp32 accumulator on every MMA, so long chains
   // drift (measured: ~50 ulp over 108 MMAs).  Each chain of <= ~12 k-steps gets its own TMEM slot and the
   // epilogue adds the chains with round-to-nearest fp32 adds.
@@ -261,6 +265,11 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     for (int c = 0; c < nchains; ++c) {
       const int last = ((c + 1) * j.nsteps) / nchains - 1;   // steps split as evenly as possible
       j.steps[last].chain_end = 1;
+    }
+    j.chain_end_mask = 0; j.half_mask = 0; j.ks_end = L.row_bytes / 32;
+    for (int s = 0; s < j.nsteps; ++s) {
+      if (j.steps[s].chain_end) j.chain_end_mask |= 1u << s;
+      if (j.steps[s].ks_begin != 0) j.half_mask |= 1u << s;
     }
   }
 }
@@ -441,6 +450,35 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     return 0;
   }
   TcLayer& L = h->tc[net][gi];
+  if (L.use_patch && h->tc_patch && (out_mode == TC_OUT_SPLIT || out_mode == TC_OUT_F32)) {
+    CUtensorMap pa_hi, pa_lo;
+    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
+    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
+    TcPatchParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.njobs = L.njobs;
+    for (int j = 0; j < L.njobs; ++j) {
+      const TcJob& src = L.jobs[j];
+      TcPatchJob& dst = pp.jobs[j];
+      dst.nsteps = src.nsteps; dst.nchains = src.nchains; dst.chain_end_mask = src.chain_end_mask;
+      dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
+      for (int s = 0; s < src.nsteps; ++s) {
+        dst.steps[s].a_off = tc_patch_a_offset(src.steps[s].dy, src.steps[s].dx);
+        dst.steps[s].w_row = src.steps[s].w_row;
+      }
+    }
+    pp.P = P; pp.n_split = n_split; pp.Hp = Hp; pp.Wp = Wp; pp.Ho = Ho; pp.Wo = Wo; pp.out_stride = L.out_stride;
+    pp.rows_per_set = L.rows_per_set;
+    pp.inv_scale[0] = L.inv_scale[0]; pp.inv_scale[1] = L.inv_scale[1];
+    pp.bias = L.bias;
+    pp.res_hi = res ? res->hi : nullptr; pp.res_lo = res ? res->lo : nullptr;
+    pp.out_mode = out_mode;
+    pp.out_hi = out.hi; pp.out_lo = out.lo;
+    pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
+    CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st,
+        launch_tc_conv_patch(pa_hi, pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
+    return 0;
+  }
   CUtensorMap ma_hi, ma_lo;
   if (int rc = make_act_map(h, &ma_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
   if (int rc = make_act_map(h, &ma_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
@@ -595,6 +633,7 @@ int nnic_create(int device, nnic_t** out) {
     return fail(nullptr, NNIC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   }
   h->encode_tiled = (EncodeTiledFn)fn;
+  if (const char* env = getenv("NNIC_TC_PATCH")) h->tc_patch = atoi(env) != 0;
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }

@@ -13,115 +13,18 @@
 //     the chains in registers with round-to-nearest fp32 adds
 //   * epilogue: 2^-k rescale, bias, leaky_relu, residual, then split-fp16 / fp32 / clamp+quantise store
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
-// warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).  Persistent: each CTA walks tiles
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator),
+// warps 2-9 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 and half of the channels).  Persistent: each CTA walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...; the ring of TMEM slots overlaps the epilogue with the MMAs.
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace nnic {
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kTileRows = 16, kTileCols = 8, kTileM = 128;
-constexpr uint64_t kWaitTimeoutCycles = 4000000000ull;   // ~2 s: a hung barrier traps instead of hanging the GPU
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if ((unsigned long long)clock64() - t0 > kWaitTimeoutCycles) {
-      if (error_flag) atomicExch(error_flag, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major operand tile whose rows are ROW_BYTES wide and swizzled with the matching TMA mode
-// (SWIZZLE_128B for 128-byte rows, SWIZZLE_64B for 64-byte rows); 8-row groups are dense.
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = ROW_BYTES == 128 ? 2ull : 4ull;     // UMMA LayoutType: SWIZZLE_128B=2, SWIZZLE_64B=4
-  constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4;                  // stride between 8-row groups
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) /*LBO (unused for swizzled K-major)*/ |
-         (sbo << 32) | (1ull << 46) /*descriptor version: Blackwell*/ | (layout << 61);
-}
-// kind::f16, A/B fp16 K-major, D fp32, M=128, N=COUT
-__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kTileM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// one lane of the (fully converged) warp; the same lane every time, so MMAs and their commits share a thread
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+constexpr int kThreads = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+using namespace tc;
 
 template <int ROW_BYTES, int COUT>
 struct TcCfg {
@@ -158,7 +61,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < Cfg::SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 4); }
+    for (int a = 0; a < Cfg::SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -218,11 +121,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int job_i = t % prm.njobs;
       const int nsteps = prm.jobs[job_i].nsteps;
+      const uint32_t chain_end_mask = prm.jobs[job_i].chain_end_mask, half_mask = prm.jobs[job_i].half_mask;
+      const int ks_full = prm.jobs[job_i].ks_end;
       bool chain_start = true;
       uint32_t d_tmem = 0;
       for (int s = 0; s < nsteps; ++s) {
-        const int ks_begin = prm.jobs[job_i].steps[s].ks_begin, ks_end = prm.jobs[job_i].steps[s].ks_end;
-        const int chain_end = prm.jobs[job_i].steps[s].chain_end;
+        const int ks_end = ks_full;
+        const int ks_begin = ((half_mask >> s) & 1u) ? (ks_full >> 1) : 0;
+        const int chain_end = (chain_end_mask >> s) & 1u;
         if (chain_start) {
           mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 2);
           d_tmem = tmem_base + slot * Cfg::SLOT_COLS;
@@ -265,9 +171,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps =====================
+    // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 (hardware restriction) and handles the channel half
+    // (w-2)/4 of those pixels, i.e. HALF = COUT/2 channels per thread.
+    constexpr int HALF = COUT / 2;
     const int lg = warp & 3;                  // TMEM lane group this warp may access
+    const int hf = (warp - 2) >> 2;           // channel half
     const int m = lg * 32 + lane;             // row of the tile = pixel
     const int r = m >> 3, c = m & 7;
+    const int ch0 = hf * HALF;
     int slot = 0; uint32_t slot_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int job_i = t % prm.njobs;
@@ -276,38 +187,36 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
       const int p = rest / tiles_per_plane;
       const int Y = (txy / tiles_x) * kTileRows + r, X = (txy % tiles_x) * kTileCols + c;
       const int set = p < prm.n_split ? 0 : 1;
-      const TcJob& job = prm.jobs[job_i];
-      const int oy = Y * prm.out_stride + job.out_oy, ox = X * prm.out_stride + job.out_ox;
+      const int nchains = prm.jobs[job_i].nchains;
+      const int oy = Y * prm.out_stride + prm.jobs[job_i].out_oy, ox = X * prm.out_stride + prm.jobs[job_i].out_ox;
       const bool valid = Y < prm.Hp && X < prm.Wp && oy < prm.Ho && ox < prm.Wo;
       const float inv_scale = prm.inv_scale[set];
-      const float* bs = bias_s + set * COUT;
+      const float* bs = bias_s + set * COUT + ch0;
       // sum the chains with round-to-nearest adds: acc += (main + correction)
-      float acc[COUT];
+      float acc[HALF];
 #pragma unroll
-      for (int i = 0; i < COUT; ++i) acc[i] = 0.0f;
-      for (int ch = 0; ch < job.nchains; ++ch) {
+      for (int i = 0; i < HALF; ++i) acc[i] = 0.0f;
+      for (int ch = 0; ch < nchains; ++ch) {
         mbar_wait(&slot_full[slot], slot_phase, error_flag, 4);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * Cfg::SLOT_COLS;
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16) {
-          float vm[16], vc[16];
-          tmem_ld16(taddr + c0, vm);
-          tmem_ld16(taddr + COUT + c0, vc);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[c0 + i] = __fadd_rn(acc[c0 + i], __fadd_rn(vm[i], vc[i]));
-        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * Cfg::SLOT_COLS + ch0;
+        uint32_t vm[HALF], vc[HALF];
+        if (HALF == 32) { tmem_ld32_nowait(taddr, vm); tmem_ld32_nowait(taddr + COUT, vc); }
+        else { tmem_ld16_nowait(taddr, vm); tmem_ld16_nowait(taddr + COUT, vc); }
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);     // the slot's data is in registers now
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
         if (++slot == Cfg::SLOTS) { slot = 0; slot_phase ^= 1; }
       }
       if (valid) {
         const size_t pix = ((size_t)p * prm.Ho + oy) * prm.Wo + ox;
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16) {
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
           float* v = acc + c0;
-          const size_t o = pix * COUT + c0;
+          const size_t o = pix * COUT + ch0 + c0;
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = leaky(__fadd_rn(v[i] * inv_scale, bs[c0 + i]));
           if (prm.res_hi) {
@@ -337,10 +246,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
               *reinterpret_cast<float4*>(prm.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
             // conv8: clip(0,1) (encoder.py:32) then np.round(e*255).astype(uint8) (encoder.py:47);
-            // latent [N,Ho,Wo,96], plane-major batch p = plane*N + n, channels plane*32 + ch
+            // latent [N,Ho,Wo,96], plane-major batch p = plane*N + n, channels plane*32 + channel
             const int N = prm.P / 3;
             const int plane = p / N, n = p - plane * N;
-            const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + c0;
+            const size_t lo_ = (((size_t)n * prm.Ho + oy) * prm.Wo + ox) * 96 + plane * 32 + ch0 + c0;
             __align__(16) uint8_t q[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) q[i] = (uint8_t)rintf(__fmul_rn(v[i], 255.0f));
