@@ -118,6 +118,8 @@ struct TcPatchParams {
   const __half* res_hi;
   const __half* res_lo;
   int out_mode;               // TC_OUT_SPLIT or TC_OUT_F32
+  long long* dbg_buf;         // development: per-CTA role timers [grid][4][8] (NNIC_TC_PROF)
+  int dbg;                    // development switches (NNIC_TC_DBG): 1 skip MMAs, 2 skip stores, 4 skip W loads, 8 skip TMEM loads
   __half* out_hi;
   __half* out_lo;
   float* out_f32;

@@ -450,7 +450,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     return 0;
   }
   TcLayer& L = h->tc[net][gi];
-  if (L.use_patch && h->tc_patch && (out_mode == TC_OUT_SPLIT || out_mode == TC_OUT_F32)) {
+  if (L.use_patch && h->tc_patch && out_mode == TC_OUT_SPLIT) {
     CUtensorMap pa_hi, pa_lo;
     if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
     if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
@@ -460,7 +460,8 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     for (int j = 0; j < L.njobs; ++j) {
       const TcJob& src = L.jobs[j];
       TcPatchJob& dst = pp.jobs[j];
-      dst.nsteps = src.nsteps; dst.nchains = src.nchains; dst.chain_end_mask = src.chain_end_mask;
+      dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 1) / 2;   // the patch kernel chains two taps per TMEM slot
+      dst.chain_end_mask = 0;
       dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
       for (int s = 0; s < src.nsteps; ++s) {
         dst.steps[s].a_off = tc_patch_a_offset(src.steps[s].dy, src.steps[s].dx);
@@ -473,10 +474,29 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.bias = L.bias;
     pp.res_hi = res ? res->hi : nullptr; pp.res_lo = res ? res->lo : nullptr;
     pp.out_mode = out_mode;
+    if (const char* env = getenv("NNIC_TC_DBG")) pp.dbg = atoi(env);
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
+    static long long* prof_buf = nullptr;
+    const bool prof = getenv("NNIC_TC_PROF") != nullptr;
+    if (prof) {
+      if (!prof_buf) cudaMalloc(&prof_buf, 148 * 4 * 8 * sizeof(long long));
+      cudaMemsetAsync(prof_buf, 0, 148 * 4 * 8 * sizeof(long long), st);
+      pp.dbg_buf = prof_buf;
+    }
     CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st,
         launch_tc_conv_patch(pa_hi, pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
+    if (prof) {
+      std::vector<long long> hb(148 * 4 * 8);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hb.data(), prof_buf, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      double a[4][8] = {};
+      for (int b = 0; b < 148; ++b) for (int r = 0; r < 4; ++r) for (int k = 0; k < 8; ++k) a[r][k] += hb[(b * 4 + r) * 8 + k] / 148.0;
+      fprintf(stderr, "[tcprof %s] producer: total %.0f wait_patch_empty %.0f wait_w_empty %.0f | mmaA: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | "
+              "mmaB: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | epi: total %.0f wait_full %.0f tmem+add %.0f out %.0f\n",
+              spec_of(net * 2, l).name, a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[1][3], a[1][4], a[2][0], a[2][1], a[2][2], a[2][3], a[2][4],
+              a[3][0], a[3][1], a[3][2], a[3][3]);
+    }
     return 0;
   }
   CUtensorMap ma_hi, ma_lo;

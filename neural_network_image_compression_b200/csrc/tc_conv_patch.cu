@@ -22,7 +22,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kThreads = 320;                 // warp 0 TMA, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int kEpiWarp0 = 2;
 constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int PATCH_TX = PH * PW * 128;                      // bytes one patch load brings: 23040
@@ -30,12 +31,19 @@ constexpr int PATCH_SLOT = (PATCH_TX + 1023) / 1024 * 1024;  // 23552
 constexpr int SET_BYTES = 2 * PATCH_SLOT;                    // hi + lo
 constexpr int NSETS = 2;
 constexpr int W_TILE = COUT * 128;                           // 8192: one of hi / lo
-constexpr int W_SLOT = 2 * W_TILE;
-constexpr int WSLOTS = 8;
+constexpr int W_SLOT = 2 * W_TILE;                           // one tap: [W_hi | W_lo]
+constexpr int GTAPS = 2;                                     // taps per accumulation chain = per weight group
+constexpr int WG_BYTES = GTAPS * W_SLOT;                     // 32 KB
+constexpr int WSLOTS = 3;                                    // weight groups in flight
+constexpr int STG_WARP = 2048;                               // per-epilogue-warp staging buffer (32 pixels x 64 B)
+constexpr int STG_BYTES = 8 * STG_WARP;
 constexpr int SLOT_COLS = 2 * COUT, SLOTS = 4, TMEM_COLS = 512;
-constexpr int BAR_OFF = NSETS * SET_BYTES + WSLOTS * W_SLOT;
+constexpr int STG_OFF = NSETS * SET_BYTES + WSLOTS * WG_BYTES;
+constexpr int BAR_OFF = STG_OFF + STG_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * COUT * 4 + 1024;
-constexpr uint32_t A_SBO = PW * 128;                         // 8-row group stride of a tap view: one patch row
+constexpr uint32_t A_SBO = PW * 128;
+
+#define TICK() ((long long)clock64())                         // 8-row group stride of a tap view: one patch row
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -48,7 +56,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patch_base = smem;                                  // [NSETS][hi | lo]
-  uint8_t* w_base = smem + NSETS * SET_BYTES;                  // [WSLOTS][W_hi | W_lo]
+  uint8_t* w_base = smem + NSETS * SET_BYTES;                  // [WSLOTS][GTAPS][W_hi | W_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* patch_full = bars;                 // [NSETS]
   uint64_t* patch_empty = bars + NSETS;        // [NSETS]
@@ -58,6 +66,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* slot_empty = slot_full + SLOTS;    // [SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 256);
+  static_assert(GTAPS == 2, "the MMA issuer keeps two tap offsets");
   static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 256, "barrier area too small");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -86,38 +95,52 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== TMA producer =====================
     int pb = 0; uint32_t pphase = 0;
     int ws = 0; uint32_t wphase = 0;
+    long long tw_patch = 0, tw_w = 0, t_begin = TICK();
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane;
       const int p = it / tiles_per_plane;
       const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
       const int set = p < prm.n_split ? 0 : 1;
-      mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1);
+      { long long t0 = TICK(); mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1); tw_patch += TICK() - t0; }
       if (elect_one()) {
         uint8_t* pbuf = patch_base + pb * SET_BYTES;
-        mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
-        tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
-        tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
+        if (prm.dbg & 16) {
+          mbar_arrive(&patch_full[pb]);
+        } else {
+          mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
+          tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
+          tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
+        }
       }
       __syncwarp();
       if (++pb == NSETS) { pb = 0; pphase ^= 1; }
       for (int j = 0; j < prm.njobs; ++j) {
         const int nsteps = prm.jobs[j].nsteps;
-        for (int s = 0; s < nsteps; ++s) {
-          const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s].w_row;
-          mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2);
+        for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one weight group = one accumulation chain
+          const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
+          { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
-            uint8_t* wb = w_base + ws * W_SLOT;
-            mbar_expect_tx(&w_full[ws], W_SLOT);
-            tma_load_2d(&map_w_hi, wb, &w_full[ws], 0, wrow);
-            tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
+            uint8_t* wb = w_base + ws * WG_BYTES;
+            if (prm.dbg & 4) {
+              mbar_arrive(&w_full[ws]);
+            } else {
+              mbar_expect_tx(&w_full[ws], ntaps * W_SLOT);
+              for (int k = 0; k < ntaps; ++k) {
+                const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s0 + k].w_row;
+                tma_load_2d(&map_w_hi, wb + k * W_SLOT, &w_full[ws], 0, wrow);
+                tma_load_2d(&map_w_lo, wb + k * W_SLOT + W_TILE, &w_full[ws], 0, wrow);
+              }
+            }
           }
           __syncwarp();
           if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+    if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 0) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_w; }
+  } else if (warp < kEpiWarp0) {
     // ===================== MMA issuer =====================
+    long long tw_patch = 0, tw_slot = 0, tw_w = 0, t_issue = 0, t_begin = TICK();
     constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
     constexpr uint32_t idesc_narrow = make_idesc(COUT);
     const uint32_t patch_u32 = smem_u32(patch_base), w_u32 = smem_u32(w_base);
@@ -125,58 +148,60 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int ws = 0; uint32_t wphase = 0;
     int slot = 0; uint32_t slot_phase = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-      mbar_wait(&patch_full[pb], pphase, error_flag, 3);
+      { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, error_flag, 3); tw_patch += TICK() - t0; }
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
       for (int j = 0; j < prm.njobs; ++j) {
         const int nsteps = prm.jobs[j].nsteps;
-        const uint32_t chain_end_mask = prm.jobs[j].chain_end_mask;
-        bool chain_start = true;
-        uint32_t d_tmem = 0;
-        for (int s = 0; s < nsteps; ++s) {
-          const uint32_t a_off = prm.jobs[j].steps[s].a_off;
-          const int chain_end = (chain_end_mask >> s) & 1u;
-          if (chain_start) {
-            mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4);
-            d_tmem = tmem_base + slot * SLOT_COLS;
-          }
-          mbar_wait(&w_full[ws], wphase, error_flag, 5);
+        for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
+          const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
+          const uint32_t a_off0 = prm.jobs[j].steps[s0].a_off;
+          const uint32_t a_off1 = prm.jobs[j].steps[s0 + ntaps - 1].a_off;
+          { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); long long t1 = TICK(); tw_slot += t1 - t0;
+            mbar_wait(&w_full[ws], wphase, error_flag, 5); tw_w += TICK() - t1; }
           tc_fence_after();
-          const uint64_t a_hi = make_desc_sbo(pset + a_off, A_SBO);
-          const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
-          const uint64_t w_hl = make_desc_sbo(w_u32 + ws * W_SLOT, 1024);   // W_hi tile followed by the W_lo tile
+          const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
+          const uint64_t w0 = make_desc_sbo(w_u32 + ws * WG_BYTES, 1024);   // tap k: + k*W_SLOT; W_hi followed by W_lo
+          const long long ti0 = TICK();
           if (elect_one()) {
-            umma_f16(d_tmem, a_hi, w_hl, idesc_wide, chain_start ? 0u : 1u);
-            umma_f16(d_tmem + COUT, a_lo, w_hl, idesc_narrow, 1u);
+            if (!(prm.dbg & 1)) {
 #pragma unroll
-            for (int ks = 1; ks < 4; ++ks) {
-              umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, 1u);
-              umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+              for (int k = 0; k < GTAPS; ++k) {
+                if (k < ntaps) {
+                  const uint64_t a_hi = make_desc_sbo(pset + (k == 0 ? a_off0 : a_off1), A_SBO);
+                  const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
+                  const uint64_t w_hl = w0 + (uint64_t)((k * W_SLOT) >> 4);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, (k | ks) ? 1u : 0u);
+                    umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                  }
+                }
+              }
             }
             umma_commit(&w_empty[ws]);
-            if (chain_end) umma_commit(&slot_full[slot]);
+            umma_commit(&slot_full[slot]);
           }
           __syncwarp();
+          t_issue += TICK() - ti0;
           if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
-          chain_start = false;
-          if (chain_end) {
-            if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
-            chain_start = true;
-          }
+          if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
         }
       }
       if (elect_one()) umma_commit(&patch_empty[pb]);      // every MMA of this work item has read the patch
       __syncwarp();
       if (++pb == NSETS) { pb = 0; pphase ^= 1; }
     }
+    if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
   } else {
     // ===================== epilogue warps =====================
     constexpr int HALF = COUT / 2;
     const int lg = warp & 3;
-    const int hf = (warp - 2) >> 2;
+    const int hf = (warp - kEpiWarp0) >> 2;
     const int m = lg * 32 + lane;
     const int r = m >> 3, c = m & 7;
     const int ch0 = hf * HALF;
     int slot = 0; uint32_t slot_phase = 0;
+    long long tw_full = 0, t_ld = 0, t_out = 0, t_begin = TICK();
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane;
       const int p = it / tiles_per_plane;
@@ -191,55 +216,111 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         float acc[HALF];
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.0f;
-        for (int ch = 0; ch < nchains; ++ch) {
-          mbar_wait(&slot_full[slot], slot_phase, error_flag, 6);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
-          uint32_t vm[HALF], vc[HALF];
-          tmem_ld32_nowait(taddr, vm);
-          tmem_ld32_nowait(taddr + COUT, vc);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&slot_empty[slot]);
+        // Global accesses of the epilogue are re-mapped through a per-warp staging buffer so that one
+        // instruction touches eight 64-byte runs (full sectors): lane l handles 16-byte piece (l & 3) of the
+        // pixel in tile row (4*lg + R), column (l >> 2), for R = 0..3.
+        uint8_t* stg = smem + STG_OFF + (warp - kEpiWarp0) * STG_WARP;
+        const int gcol = lane >> 2, gpiece = lane & 3;
+        size_t goff[4];                     // element offset of this lane's piece for R = 0..3, or ~0 when outside
 #pragma unroll
-          for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
-          if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+        for (int R = 0; R < 4; ++R) {
+          const int gY = (txy / tiles_x) * kTileRows + lg * 4 + R, gX = (txy % tiles_x) * kTileCols + gcol;
+          const int goy = gY * prm.out_stride + prm.jobs[j].out_oy, gox = gX * prm.out_stride + prm.jobs[j].out_ox;
+          const bool gvalid = gY < prm.Hp && gX < prm.Wp && goy < prm.Ho && gox < prm.Wo;
+          goff[R] = gvalid ? (((size_t)p * prm.Ho + goy) * prm.Wo + gox) * COUT + ch0 + gpiece * 8 : ~(size_t)0;
         }
-        if (valid) {
-          const size_t pix = ((size_t)p * prm.Ho + oy) * prm.Wo + ox;
+        // residual: coalesced loads now (latency hides behind the MMAs), redistributed to the owning lanes later
+        uint4 res_h[4], res_l[4];
+        const bool has_res = prm.res_hi != nullptr;
+        if (has_res) {
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 16) {
-            float* v = acc + c0;
-            const size_t o = pix * COUT + ch0 + c0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = leaky(__fadd_rn(v[i] * inv_scale, bs[c0 + i]));
-            if (prm.res_hi) {
-              __align__(16) __half rh[16], rl[16];
-              *reinterpret_cast<uint4*>(rh) = *reinterpret_cast<const uint4*>(prm.res_hi + o);
-              *reinterpret_cast<uint4*>(rh + 8) = *reinterpret_cast<const uint4*>(prm.res_hi + o + 8);
-              *reinterpret_cast<uint4*>(rl) = *reinterpret_cast<const uint4*>(prm.res_lo + o);
-              *reinterpret_cast<uint4*>(rl + 8) = *reinterpret_cast<const uint4*>(prm.res_lo + o + 8);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], join_f32(rh[i], rl[i]));
-            }
-            if (prm.out_mode == TC_OUT_SPLIT) {
-              __align__(16) __half h[16], l[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) split_f32(v[i], h[i], l[i]);
-              *reinterpret_cast<uint4*>(prm.out_hi + o) = *reinterpret_cast<uint4*>(h);
-              *reinterpret_cast<uint4*>(prm.out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 8);
-              *reinterpret_cast<uint4*>(prm.out_lo + o) = *reinterpret_cast<uint4*>(l);
-              *reinterpret_cast<uint4*>(prm.out_lo + o + 8) = *reinterpret_cast<uint4*>(l + 8);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4*>(prm.out_f32 + o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int R = 0; R < 4; ++R) {
+            res_h[R] = make_uint4(0, 0, 0, 0); res_l[R] = make_uint4(0, 0, 0, 0);
+            if (goff[R] != ~(size_t)0) {
+              res_h[R] = *reinterpret_cast<const uint4*>(prm.res_hi + goff[R]);
+              res_l[R] = *reinterpret_cast<const uint4*>(prm.res_lo + goff[R]);
             }
           }
         }
+        for (int ch = 0; ch < nchains; ++ch) {
+          long long te0 = TICK();
+          mbar_wait(&slot_full[slot], slot_phase, error_flag, 6);
+          long long te1 = TICK(); tw_full += te1 - te0;
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
+          uint32_t vm[HALF], vc[HALF];
+          if (prm.dbg & 8) {
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) { vm[i] = 0; vc[i] = 0; }
+          } else {
+            tmem_ld32_nowait(taddr, vm);
+            tmem_ld32_nowait(taddr + COUT, vc);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_empty[slot]);
+          if (!(prm.dbg & 32)) {
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
+          }
+          if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+          t_ld += TICK() - te1;
+        }
+        const long long to0 = TICK();
+        if (!(prm.dbg & 2)) {
+          // piece j of lane i lives at i*64 + ((j ^ (i >> 1)) & 3)*16: conflict-free for both access patterns
+          auto stg_own = [&](int j) { return reinterpret_cast<uint4*>(stg + lane * 64 + (((j ^ (lane >> 1)) & 3) << 4)); };
+          auto stg_grp = [&](int R) { const int q = R * 8 + gcol; return reinterpret_cast<uint4*>(stg + q * 64 + (((gpiece ^ (q >> 1)) & 3) << 4)); };
+          float rsum[HALF];
+          if (has_res) {
+            // hi pieces -> owners, then lo pieces -> owners
+            uint4 own_h[4], own_l[4];
+#pragma unroll
+            for (int R = 0; R < 4; ++R) *stg_grp(R) = res_h[R];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) own_h[q] = *stg_own(q);
+            __syncwarp();
+#pragma unroll
+            for (int R = 0; R < 4; ++R) *stg_grp(R) = res_l[R];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) own_l[q] = *stg_own(q);
+            __syncwarp();
+            const __half* rh = reinterpret_cast<const __half*>(own_h);
+            const __half* rl = reinterpret_cast<const __half*>(own_l);
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) rsum[i] = join_f32(rh[i], rl[i]);
+          }
+          __align__(16) __half h[HALF], l[HALF];
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) {
+            float v = leaky(__fadd_rn(acc[i] * inv_scale, bs[i]));
+            if (has_res) v = __fadd_rn(v, rsum[i]);
+            split_f32(v, h[i], l[i]);
+          }
+          if (prm.out_mode == TC_OUT_SPLIT) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *stg_own(q) = reinterpret_cast<uint4*>(h)[q];
+            __syncwarp();
+#pragma unroll
+            for (int R = 0; R < 4; ++R)
+              if (goff[R] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_hi + goff[R]) = *stg_grp(R);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *stg_own(q) = reinterpret_cast<uint4*>(l)[q];
+            __syncwarp();
+#pragma unroll
+            for (int R = 0; R < 4; ++R)
+              if (goff[R] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_lo + goff[R]) = *stg_grp(R);
+            __syncwarp();
+          }
+        }
+        t_out += TICK() - to0;
       }
     }
+    if (prm.dbg_buf && lane == 0 && warp == kEpiWarp0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 3) * 8; o[0] = TICK() - t_begin; o[1] = tw_full; o[2] = t_ld; o[3] = t_out; }
   }
 
   tc_fence_before();
