@@ -130,4 +130,20 @@ cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_l
                                  const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                  cudaStream_t stream);
 
+// ---- dconv8 + colour inverse + pack on the tensor cores (tc_dconv8.cu) ------------------------------
+struct TcDconv8Params {
+  int N, Hi, Wi;              // images, input size (output is 2Hi x 2Wi)
+  float inv_scale[2];         // 2^-(ka+kw) per weight set
+  float bias[2];
+  ColourConsts cc;
+  uint8_t* rgb;               // optional u8 [N,2Hi,2Wi,3]
+  float* prequant;            // optional f32 [N,2Hi,2Wi,3]
+  float* planes_out;          // optional f32 [3][N,2Hi,2Wi,1]
+};
+// a_hi / a_lo: plain views of the split-fp16 input [3N,Hi,Wi,64] with box [64, 8, 1, 16, 1];
+// w_hi / w_lo: [2 sets x 32 taps (25 used)][64] fp16 matrices with box [64, 32]
+cudaError_t launch_tc_dconv8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                             const CUtensorMap& w_lo, const TcDconv8Params& prm, int num_sms, int* error_flag,
+                             cudaStream_t stream);
+
 }  // namespace nnic

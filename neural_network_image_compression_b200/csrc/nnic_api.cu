@@ -71,6 +71,7 @@ struct nnic_handle {
   std::string err;
   uint64_t launches = 0;
   int micro_batch = 0;
+  bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   bool tc_patch = true;             // use the halo-patch kernel where it applies (NNIC_TC_PATCH=0 disables)
   EncodeTiledFn encode_tiled = nullptr;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
@@ -85,6 +86,10 @@ struct nnic_handle {
   std::vector<float> w_edge[2];            // host: conv1 [2][25][32] / dconv8 [2][25][64] (passed as kernel parameters)
   std::vector<float> b_edge[2];            // host: [2][32] / [2][1]
   TcLayer tc[2][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7
+  // dconv8 on the tensor cores: [2 sets][32 taps][64 ci] fp16 hi/lo
+  __half* d8_w_hi = nullptr; __half* d8_w_lo = nullptr;
+  CUtensorMap d8_map_w_hi, d8_map_w_lo;
+  float d8_inv_scale[2] = {1.f, 1.f};
   SimtLayer simt[2][4];
 
   // scratch arena
@@ -315,6 +320,36 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
     }
     h->w_edge[net] = w;
     h->b_edge[net] = b;
+    if (net == 1) {
+      // tensor-core form of dconv8: rows = taps (25 of 32 used), columns = input channels
+      std::vector<__half> whi(2 * 32 * 64, __float2half_rn(0.f)), wlo(2 * 32 * 64, __float2half_rn(0.f));
+      for (int s = 0; s < 2; ++s) {
+        float maxabs = 0.f;
+        for (int i = 0; i < per; ++i) maxabs = fmaxf(maxabs, fabsf(w[s * per + i]));
+        int kexp = 0;
+        if (maxabs > 0.f && std::isfinite(maxabs)) {
+          kexp = (int)floorf(log2f(32768.0f / maxabs));
+          if (kexp < -14) kexp = -14;
+          if (kexp > 24) kexp = 24;
+        }
+        const float scale = ldexpf(1.0f, kexp);
+        h->d8_inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
+        for (int t = 0; t < 25; ++t)
+          for (int c = 0; c < 64; ++c) {
+            const float v = w[s * per + t * 64 + c] * scale;
+            const __half hi = __float2half_rn(v);
+            whi[(s * 32 + t) * 64 + c] = hi;
+            wlo[(s * 32 + t) * 64 + c] = __float2half_rn(v - __half2float(hi));
+          }
+      }
+      if (int rc = upload(h, (void**)&h->d8_w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
+      if (int rc = upload(h, (void**)&h->d8_w_lo, wlo.data(), wlo.size() * sizeof(__half))) return rc;
+      cuuint64_t dims[2] = {64, 64};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, 32};
+      if (int rc = make_map(h, &h->d8_map_w_hi, h->d8_w_hi, 2, dims, strides, box, 128)) return rc;
+      if (int rc = make_map(h, &h->d8_map_w_lo, h->d8_w_lo, 2, dims, strides, box, 128)) return rc;
+    }
   }
   for (int gi = 0; gi < 4; ++gi) {
     const int l = net == 0 ? gi + 1 : gi;
@@ -597,7 +632,21 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
-  CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
+  if (split && h->tc_dconv8) {
+    CUtensorMap ma_hi, ma_lo;
+    if (int rc = make_act_map(h, &ma_hi, d4.hi, P, 4 * lh, 4 * lw, 64, false, 64, 128)) return rc;
+    if (int rc = make_act_map(h, &ma_lo, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128)) return rc;
+    TcDconv8Params dp;
+    memset(&dp, 0, sizeof dp);
+    dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
+    dp.inv_scale[0] = h->d8_inv_scale[0]; dp.inv_scale[1] = h->d8_inv_scale[1];
+    dp.bias[0] = h->b_edge[1][0]; dp.bias[1] = h->b_edge[1][1];
+    dp.cc = colour_consts();
+    dp.rgb = rgb; dp.prequant = prequant; dp.planes_out = out_planes;
+    CKL(h, K_DCONV8, st, launch_tc_dconv8(ma_hi, ma_lo, h->d8_map_w_hi, h->d8_map_w_lo, dp, h->num_sms, h->error_flag_dev, st));
+  } else {
+    CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
+  }
   record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
   h->arena_used = base_used;
   return 0;
@@ -654,6 +703,7 @@ int nnic_create(int device, nnic_t** out) {
   }
   h->encode_tiled = (EncodeTiledFn)fn;
   if (const char* env = getenv("NNIC_TC_PATCH")) h->tc_patch = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
@@ -671,6 +721,7 @@ void nnic_destroy(nnic_t* h) {
       cudaFree(h->simt[n][i].w); cudaFree(h->simt[n][i].bias);
     }
   }
+  cudaFree(h->d8_w_hi); cudaFree(h->d8_w_lo);
   cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
   if (h->error_flag_host) cudaFreeHost(h->error_flag_host);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
