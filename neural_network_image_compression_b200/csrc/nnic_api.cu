@@ -495,7 +495,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     for (int j = 0; j < L.njobs; ++j) {
       const TcJob& src = L.jobs[j];
       TcPatchJob& dst = pp.jobs[j];
-      dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 1) / 2;   // the patch kernel chains two taps per TMEM slot
+      dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 2) / 3;   // the patch kernel chains three taps per TMEM slot
       dst.chain_end_mask = 0;
       dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
       for (int s = 0; s < src.nsteps; ++s) {

@@ -32,9 +32,9 @@ constexpr int SET_BYTES = 2 * PATCH_SLOT;                    // hi + lo
 constexpr int NSETS = 2;
 constexpr int W_TILE = COUT * 128;                           // 8192: one of hi / lo
 constexpr int W_SLOT = 2 * W_TILE;                           // one tap: [W_hi | W_lo]
-constexpr int GTAPS = 2;                                     // taps per accumulation chain = per weight group
+constexpr int GTAPS = 3;                                     // taps per accumulation chain = per weight group
 constexpr int WG_BYTES = GTAPS * W_SLOT;                     // 32 KB
-constexpr int WSLOTS = 3;                                    // weight groups in flight
+constexpr int WSLOTS = 2;                                    // weight groups in flight
 constexpr int STG_WARP = 2048;                               // per-epilogue-warp staging buffer (32 pixels x 64 B)
 constexpr int STG_BYTES = 8 * STG_WARP;
 constexpr int SLOT_COLS = 2 * COUT, SLOTS = 4, TMEM_COLS = 512;
@@ -66,7 +66,6 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* slot_empty = slot_full + SLOTS;    // [SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 256);
-  static_assert(GTAPS == 2, "the MMA issuer keeps two tap offsets");
   static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 256, "barrier area too small");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -154,8 +153,9 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int nsteps = prm.jobs[j].nsteps;
         for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
           const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
-          const uint32_t a_off0 = prm.jobs[j].steps[s0].a_off;
-          const uint32_t a_off1 = prm.jobs[j].steps[s0 + ntaps - 1].a_off;
+          uint32_t a_off[GTAPS];
+#pragma unroll
+          for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
           { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); long long t1 = TICK(); tw_slot += t1 - t0;
             mbar_wait(&w_full[ws], wphase, error_flag, 5); tw_w += TICK() - t1; }
           tc_fence_after();
@@ -167,7 +167,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
               for (int k = 0; k < GTAPS; ++k) {
                 if (k < ntaps) {
-                  const uint64_t a_hi = make_desc_sbo(pset + (k == 0 ? a_off0 : a_off1), A_SBO);
+                  const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
                   const uint64_t w_hl = w0 + (uint64_t)((k * W_SLOT) >> 4);
 #pragma unroll
