@@ -22,8 +22,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 320;                 // warp 0 TMA, warp 1 MMA issuer, warps 2-9 epilogue
-constexpr int kEpiWarp0 = 2;
+constexpr int kThreads = 384;                 // warp 0 weight TMA, warps 1-2 MMA issuers, warps 3-10 epilogue, warp 11 patch TMA
+constexpr int kEpiWarp0 = 3;
+constexpr int kPatchWarp = 11;
 constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int PATCH_TX = PH * PW * 128;                      // bytes one patch load brings: 23040
@@ -72,7 +73,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 1); }
+    for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 2); }
     for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,17 +91,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = tiles_x * tiles_y;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == kPatchWarp) {
+    // ===================== TMA producer: activation patches =====================
     int pb = 0; uint32_t pphase = 0;
-    int ws = 0; uint32_t wphase = 0;
-    long long tw_patch = 0, tw_w = 0, t_begin = TICK();
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-      const int txy = it % tiles_per_plane;
-      const int p = it / tiles_per_plane;
+      const int txy = it % tiles_per_plane, p = it / tiles_per_plane;
       const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
-      const int set = p < prm.n_split ? 0 : 1;
-      { long long t0 = TICK(); mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1); tw_patch += TICK() - t0; }
+      mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1);
       if (elect_one()) {
         uint8_t* pbuf = patch_base + pb * SET_BYTES;
         if (prm.dbg & 16) {
@@ -113,6 +110,14 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
       __syncwarp();
       if (++pb == NSETS) { pb = 0; pphase ^= 1; }
+    }
+  } else if (warp == 0) {
+    // ===================== TMA producer: weight groups =====================
+    int ws = 0; uint32_t wphase = 0;
+    long long tw_patch = 0, tw_w = 0, t_begin = TICK();
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int p = it / tiles_per_plane;
+      const int set = p < prm.n_split ? 0 : 1;
       for (int j = 0; j < prm.njobs; ++j) {
         const int nsteps = prm.jobs[j].nsteps;
         for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one weight group = one accumulation chain
@@ -139,6 +144,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 0) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_w; }
   } else if (warp < kEpiWarp0) {
     // ===================== MMA issuer =====================
+    const int my_parity = warp - 1;          // two issuers take alternate chains
+    int chain_ctr = 0;
     long long tw_patch = 0, tw_slot = 0, tw_w = 0, t_issue = 0, t_begin = TICK();
     constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
     constexpr uint32_t idesc_narrow = make_idesc(COUT);
@@ -153,6 +160,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int nsteps = prm.jobs[j].nsteps;
         for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
           const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
+          if (((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
+            if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
+            if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+            continue;
+          }
           uint32_t a_off[GTAPS];
 #pragma unroll
           for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
