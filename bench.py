@@ -103,8 +103,7 @@ def cpu_reference_sample(workload, n_images, threads=None):
     import torch
     from neural_network_image_compression_b200 import weights as Wt
     from oracle import nnic_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)     # torchrun sets OMP_NUM_THREADS=1; use every host core
     cores = torch.get_num_threads()
     _n, H, W, stages, _d = WORKLOADS[workload]
     rng = np.random.default_rng(0)
@@ -147,10 +146,23 @@ def run_reference(args):
            "cpu_baseline": {"value": round(value, 4), "unit": "MP/s", "cores": cores, "kind": "port", "sample": text},
            "e2e": {"value": round(value, 4), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "CPU restatement of the reference (oracle/), not TensorFlow: TensorFlow is not installable here"}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)          # libraries that print to fd 1 (e.g. the NCCL version banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -337,7 +349,7 @@ def main():
                    "steps": e2e_steps, "api": "Encoder()(x) / rate() / Decoder()(x) on pinned NumPy buffers"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
            "cpu_baseline": cpu_baseline}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 

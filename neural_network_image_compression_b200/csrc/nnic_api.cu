@@ -92,6 +92,10 @@ struct nnic_handle {
   float d8_inv_scale[2] = {1.f, 1.f};
   SimtLayer simt[2][4];
 
+  // host-buffer calls: copies run on two internal streams and overlap the kernels of neighbouring micro-batches
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+
   // scratch arena
   DevBuf arena;
   size_t arena_used = 0;
@@ -707,6 +711,13 @@ int nnic_create(int device, nnic_t** out) {
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
+  bool ok = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { nnic_destroy(h); return fail(nullptr, NNIC_ERR_CUDA, "stream / event creation failed"); }
   *out = h;
   return NNIC_OK;
 }
@@ -723,6 +734,9 @@ void nnic_destroy(nnic_t* h) {
   }
   cudaFree(h->d8_w_hi); cudaFree(h->d8_w_lo);
   cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
   if (h->error_flag_host) cudaFreeHost(h->error_flag_host);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
@@ -773,33 +787,47 @@ int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* lat
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
   const int lh = (H + 7) / 8, lw = (W + 7) / 8;
   const size_t img_px = (size_t)H * W, lat_px = (size_t)lh * lw;
-  const int mb = pick_micro_batch(h, N, img_px);
   const bool host = mem_kind == NNIC_MEM_HOST;
+  int mb = pick_micro_batch(h, N, img_px);
+  if (host && h->micro_batch == 0 && N >= 2) {      // at least ~4 micro-batches so copies overlap the kernels
+    const int quarter = (N + 3) / 4;
+    if (quarter < mb) mb = quarter;
+  }
   size_t need = enc_act_need(split, 3 * (size_t)mb, H, W);
-  if (host) need += pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * lat_px * 96 * 4) : 0) + 4096;
+  if (host) need += 2 * (pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * lat_px * 96 * 4) : 0)) + 8192;
   if (int rc = ensure_buf(h, h->arena, need)) return rc;
   h->arena_used = 0;
-  uint8_t *d_rgb = nullptr, *d_lat = nullptr; float* d_pre = nullptr;
+  uint8_t *d_rgb[2] = {nullptr, nullptr}, *d_lat[2] = {nullptr, nullptr}; float* d_pre[2] = {nullptr, nullptr};
   if (host) {
-    d_rgb = (uint8_t*)arena_take(h, mb * img_px * 3);
-    d_lat = (uint8_t*)arena_take(h, mb * lat_px * 96);
-    if (prequant) d_pre = (float*)arena_take(h, mb * lat_px * 96 * 4);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      d_rgb[s2] = (uint8_t*)arena_take(h, mb * img_px * 3);
+      d_lat[s2] = (uint8_t*)arena_take(h, mb * lat_px * 96);
+      if (prequant) d_pre[s2] = (float*)arena_take(h, mb * lat_px * 96 * 4);
+    }
   }
-  for (int i0 = 0; i0 < N; i0 += mb) {
+  int idx = 0;
+  for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
     const int nb = (N - i0) < mb ? (N - i0) : mb;
     const uint8_t* src = rgb + (size_t)i0 * img_px * 3;
     uint8_t* dst = latent + (size_t)i0 * lat_px * 96;
     float* pre = prequant ? prequant + (size_t)i0 * lat_px * 96 : nullptr;
     if (host) {
-      CK(h, cudaMemcpyAsync(d_rgb, src, nb * img_px * 3, cudaMemcpyHostToDevice, st));
-      if (int rc = encode_batch(h, d_rgb, nullptr, nb, H, W, d_lat, d_pre, nullptr, st)) return rc;
-      CK(h, cudaMemcpyAsync(dst, d_lat, nb * lat_px * 96, cudaMemcpyDeviceToHost, st));
-      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre, nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, st));
+      const int s2 = idx & 1;
+      if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));   // staging set s2 is drained
+      CK(h, cudaMemcpyAsync(d_rgb[s2], src, nb * img_px * 3, cudaMemcpyHostToDevice, h->h2d_stream));
+      CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
+      CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
+      if (int rc = encode_batch(h, d_rgb[s2], nullptr, nb, H, W, d_lat[s2], d_pre[s2], nullptr, st)) return rc;
+      CK(h, cudaEventRecord(h->ev_comp[s2], st));
+      CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
+      CK(h, cudaMemcpyAsync(dst, d_lat[s2], nb * lat_px * 96, cudaMemcpyDeviceToHost, h->d2h_stream));
+      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+      CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
     } else {
       if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, st)) return rc;
     }
   }
-  if (host) { CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
+  if (host) { CK(h, cudaStreamSynchronize(h->d2h_stream)); CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
   return NNIC_OK;
 }
 
@@ -814,33 +842,47 @@ int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
   const size_t img_px = (size_t)lh * lw * 64, lat_px = (size_t)lh * lw;
-  const int mb = pick_micro_batch(h, N, img_px);
   const bool host = mem_kind == NNIC_MEM_HOST;
+  int mb = pick_micro_batch(h, N, img_px);
+  if (host && h->micro_batch == 0 && N >= 2) {
+    const int quarter = (N + 3) / 4;
+    if (quarter < mb) mb = quarter;
+  }
   size_t need = dec_act_need(split, 3 * (size_t)mb, lh, lw);
-  if (host) need += pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * img_px * 3 * 4) : 0) + 4096;
+  if (host) need += 2 * (pad1k(mb * img_px * 3) + pad1k(mb * lat_px * 96) + (prequant ? pad1k(mb * img_px * 3 * 4) : 0)) + 8192;
   if (int rc = ensure_buf(h, h->arena, need)) return rc;
   h->arena_used = 0;
-  uint8_t *d_rgb = nullptr, *d_lat = nullptr; float* d_pre = nullptr;
+  uint8_t *d_rgb[2] = {nullptr, nullptr}, *d_lat[2] = {nullptr, nullptr}; float* d_pre[2] = {nullptr, nullptr};
   if (host) {
-    d_rgb = (uint8_t*)arena_take(h, mb * img_px * 3);
-    d_lat = (uint8_t*)arena_take(h, mb * lat_px * 96);
-    if (prequant) d_pre = (float*)arena_take(h, mb * img_px * 3 * 4);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      d_rgb[s2] = (uint8_t*)arena_take(h, mb * img_px * 3);
+      d_lat[s2] = (uint8_t*)arena_take(h, mb * lat_px * 96);
+      if (prequant) d_pre[s2] = (float*)arena_take(h, mb * img_px * 3 * 4);
+    }
   }
-  for (int i0 = 0; i0 < N; i0 += mb) {
+  int idx = 0;
+  for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
     const int nb = (N - i0) < mb ? (N - i0) : mb;
     const uint8_t* src = latent + (size_t)i0 * lat_px * 96;
     uint8_t* dst = rgb + (size_t)i0 * img_px * 3;
     float* pre = prequant ? prequant + (size_t)i0 * img_px * 3 : nullptr;
     if (host) {
-      CK(h, cudaMemcpyAsync(d_lat, src, nb * lat_px * 96, cudaMemcpyHostToDevice, st));
-      if (int rc = decode_batch(h, d_lat, nullptr, nb, lh, lw, d_rgb, d_pre, nullptr, st)) return rc;
-      CK(h, cudaMemcpyAsync(dst, d_rgb, nb * img_px * 3, cudaMemcpyDeviceToHost, st));
-      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre, nb * img_px * 3 * 4, cudaMemcpyDeviceToHost, st));
+      const int s2 = idx & 1;
+      if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));
+      CK(h, cudaMemcpyAsync(d_lat[s2], src, nb * lat_px * 96, cudaMemcpyHostToDevice, h->h2d_stream));
+      CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
+      CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
+      if (int rc = decode_batch(h, d_lat[s2], nullptr, nb, lh, lw, d_rgb[s2], d_pre[s2], nullptr, st)) return rc;
+      CK(h, cudaEventRecord(h->ev_comp[s2], st));
+      CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
+      CK(h, cudaMemcpyAsync(dst, d_rgb[s2], nb * img_px * 3, cudaMemcpyDeviceToHost, h->d2h_stream));
+      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * img_px * 3 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+      CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
     } else {
       if (int rc = decode_batch(h, src, nullptr, nb, lh, lw, dst, pre, nullptr, st)) return rc;
     }
   }
-  if (host) { CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
+  if (host) { CK(h, cudaStreamSynchronize(h->d2h_stream)); CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
   return NNIC_OK;
 }
 
