@@ -130,6 +130,22 @@ cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_l
                                  const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                  cudaStream_t stream);
 
+// ---- colour + conv1 on the tensor cores (tc_conv1.cu) ----------------------------------------------
+struct TcConv1Params {
+  const uint8_t* rgb;         // u8 [N,H,W,3] (colour transform fused), or
+  const float* planes;        // f32 [3N,H,W,1]
+  int N, H, W, Ho, Wo, pad_t, pad_l;
+  const __half* w_hi;         // device [2 sets][32 channels][32 taps (25 used)] fp16, scaled
+  const __half* w_lo;
+  const float* bias;          // device [2][32]
+  float inv_scale[2];
+  ColourConsts cc;
+  __half* out_hi;             // split fp16 [3N,Ho,Wo,32] ...
+  __half* out_lo;
+  float* out_f32;             // ... or fp32
+};
+cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_flag, cudaStream_t stream);
+
 // ---- dconv8 + colour inverse + pack on the tensor cores (tc_dconv8.cu) ------------------------------
 struct TcDconv8Params {
   int N, Hi, Wi;              // images, input size (output is 2Hi x 2Wi)

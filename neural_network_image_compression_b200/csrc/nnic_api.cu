@@ -86,6 +86,10 @@ struct nnic_handle {
   std::vector<float> w_edge[2];            // host: conv1 [2][25][32] / dconv8 [2][25][64] (passed as kernel parameters)
   std::vector<float> b_edge[2];            // host: [2][32] / [2][1]
   TcLayer tc[2][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7
+  // conv1 on the tensor cores: [2 sets][32 channels][32 taps] fp16 hi/lo, bias [2][32]
+  __half* c1_w_hi = nullptr; __half* c1_w_lo = nullptr; float* c1_bias = nullptr;
+  float c1_inv_scale[2] = {1.f, 1.f};
+  bool tc_conv1 = true;             // conv1 on the tensor cores (NNIC_TC_CONV1=0: FFMA kernel)
   // dconv8 on the tensor cores: [2 sets][32 taps][64 ci] fp16 hi/lo
   __half* d8_w_hi = nullptr; __half* d8_w_lo = nullptr;
   CUtensorMap d8_map_w_hi, d8_map_w_lo;
@@ -324,6 +328,32 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
     }
     h->w_edge[net] = w;
     h->b_edge[net] = b;
+    if (net == 0) {
+      // tensor-core form of conv1: rows = output channels, columns = taps (25 of 32 used)
+      std::vector<__half> whi(2 * 32 * 32, __float2half_rn(0.f)), wlo(2 * 32 * 32, __float2half_rn(0.f));
+      for (int s = 0; s < 2; ++s) {
+        float maxabs = 0.f;
+        for (int i = 0; i < per; ++i) maxabs = fmaxf(maxabs, fabsf(w[s * per + i]));
+        int kexp = 0;
+        if (maxabs > 0.f && std::isfinite(maxabs)) {
+          kexp = (int)floorf(log2f(32768.0f / maxabs));
+          if (kexp < -14) kexp = -14;
+          if (kexp > 24) kexp = 24;
+        }
+        const float scale = ldexpf(1.0f, kexp);
+        h->c1_inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
+        for (int t = 0; t < 25; ++t)
+          for (int c = 0; c < 32; ++c) {
+            const float v = w[s * per + t * 32 + c] * scale;
+            const __half hi = __float2half_rn(v);
+            whi[(s * 32 + c) * 32 + t] = hi;
+            wlo[(s * 32 + c) * 32 + t] = __float2half_rn(v - __half2float(hi));
+          }
+      }
+      if (int rc = upload(h, (void**)&h->c1_w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
+      if (int rc = upload(h, (void**)&h->c1_w_lo, wlo.data(), wlo.size() * sizeof(__half))) return rc;
+      if (int rc = upload(h, (void**)&h->c1_bias, b.data(), b.size() * 4)) return rc;
+    }
     if (net == 1) {
       // tensor-core form of dconv8: rows = taps (25 of 32 used), columns = input channels
       std::vector<__half> whi(2 * 32 * 64, __float2half_rn(0.f)), wlo(2 * 32 * 64, __float2half_rn(0.f));
@@ -587,7 +617,20 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
   Act a3 = take_act(h, split, P, H2, W2, 64);
   Act a4 = take_act(h, split, P, H2, W2, 64);
   Act a5; a5.H = H3; a5.W = W3; a5.C = 32;
-  CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0].data(), h->b_edge[0].data(), a1.hi, a1.lo, a1.f32, st));
+  if (split && h->tc_conv1) {
+    TcConv1Params cp;
+    memset(&cp, 0, sizeof cp);
+    cp.rgb = rgb; cp.planes = planes; cp.N = nb; cp.H = H; cp.W = W; cp.Ho = H1; cp.Wo = W1;
+    int tmp;
+    same_pad(H, 5, 2, tmp, cp.pad_t); same_pad(W, 5, 2, tmp, cp.pad_l);
+    cp.w_hi = h->c1_w_hi; cp.w_lo = h->c1_w_lo; cp.bias = h->c1_bias;
+    cp.inv_scale[0] = h->c1_inv_scale[0]; cp.inv_scale[1] = h->c1_inv_scale[1];
+    cp.cc = colour_consts();
+    cp.out_hi = a1.hi; cp.out_lo = a1.lo;
+    CKL(h, K_CONV1, st, launch_tc_conv1(cp, h->num_sms, h->error_flag_dev, st));
+  } else {
+    CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0].data(), h->b_edge[0].data(), a1.hi, a1.lo, a1.f32, st));
+  }
   if (int rc = run_gemm_layer(h, 0, 0, a1, a2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 1, a2, a3, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 0, 2, a3, a4, &a2, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
@@ -708,6 +751,7 @@ int nnic_create(int device, nnic_t** out) {
   h->encode_tiled = (EncodeTiledFn)fn;
   if (const char* env = getenv("NNIC_TC_PATCH")) h->tc_patch = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
@@ -733,6 +777,7 @@ void nnic_destroy(nnic_t* h) {
     }
   }
   cudaFree(h->d8_w_hi); cudaFree(h->d8_w_lo);
+  cudaFree(h->c1_w_hi); cudaFree(h->c1_w_lo); cudaFree(h->c1_bias);
   cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);

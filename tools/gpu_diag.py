@@ -53,6 +53,7 @@ def main():
         enc.set_weights(0, wsets["encY"]); enc.set_weights(1, wsets["encCbCr"])
         dec = nn.Decoder(0, arith)
         dec.set_weights(0, wsets["decY"]); dec.set_weights(1, wsets["decCbCr"])
+        enc.handle.set_micro_batch(N); dec.handle.set_micro_batch(N)   # one micro-batch, so debug_fetch sees every image
         sym, pre = enc(img, return_prequant=True)
         print(f"  encode done in {time.time() - t0:.2f}s; launches {enc.handle.launch_count}", flush=True)
         for slot, nm in enumerate(["conv1", "conv2", "conv3", "conv4+res"]):
