@@ -233,13 +233,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], 0.0f), 1.0f);
           }
           if (prm.out_mode == TC_OUT_SPLIT) {
-            __align__(16) __half h[16], l[16];
+            __align__(16) uint32_t h[8], l[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_f32(v[i], h[i], l[i]);
+            for (int i = 0; i < 16; i += 2) split2_f32(v[i], v[i + 1], h[i / 2], l[i / 2]);
             *reinterpret_cast<uint4*>(prm.out_hi + o) = *reinterpret_cast<uint4*>(h);
-            *reinterpret_cast<uint4*>(prm.out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 8);
+            *reinterpret_cast<uint4*>(prm.out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 4);
             *reinterpret_cast<uint4*>(prm.out_lo + o) = *reinterpret_cast<uint4*>(l);
-            *reinterpret_cast<uint4*>(prm.out_lo + o + 8) = *reinterpret_cast<uint4*>(l + 8);
+            *reinterpret_cast<uint4*>(prm.out_lo + o + 8) = *reinterpret_cast<uint4*>(l + 4);
           } else if (prm.out_mode == TC_OUT_F32) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)

@@ -233,11 +233,12 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
       const float inv_scale = prm.inv_scale[set];
       const float* bs = bias_s + set * CO + ch0;
-      __align__(16) __half h[HALF], l[HALF];
+      __align__(16) uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-      for (int i = 0; i < HALF; ++i) {
-        const float v = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])) * inv_scale, bs[i]));
-        split_f32(v, h[i], l[i]);
+      for (int i = 0; i < HALF; i += 2) {
+        const float v0 = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])) * inv_scale, bs[i]));
+        const float v1 = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i + 1]), __uint_as_float(vc[i + 1])) * inv_scale, bs[i + 1]));
+        split2_f32(v0, v1, h[i / 2], l[i / 2]);
       }
       // in instruction i, lane l stores 16-byte piece (l & 1) of pixel i*16 + (l >> 1) of this warp's 32 pixels
       size_t goff[2];

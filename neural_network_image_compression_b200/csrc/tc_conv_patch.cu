@@ -305,12 +305,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int i = 0; i < HALF; ++i) rsum[i] = join_f32(rh[i], rl[i]);
           }
-          __align__(16) __half h[HALF], l[HALF];
+          __align__(16) uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-          for (int i = 0; i < HALF; ++i) {
-            float v = leaky(__fadd_rn(acc[i] * inv_scale, bs[i]));
-            if (has_res) v = __fadd_rn(v, rsum[i]);
-            split_f32(v, h[i], l[i]);
+          for (int i = 0; i < HALF; i += 2) {
+            float v0 = leaky(__fadd_rn(acc[i] * inv_scale, bs[i]));
+            float v1 = leaky(__fadd_rn(acc[i + 1] * inv_scale, bs[i + 1]));
+            if (has_res) { v0 = __fadd_rn(v0, rsum[i]); v1 = __fadd_rn(v1, rsum[i + 1]); }
+            split2_f32(v0, v1, h[i / 2], l[i / 2]);
           }
           if (prm.out_mode == TC_OUT_SPLIT) {
 #pragma unroll
