@@ -93,8 +93,8 @@ cudaError_t launch_tc_conv(int row_bytes, int cout, const CUtensorMap& a_hi, con
                            const CUtensorMap& w_hi, const CUtensorMap& w_lo, const TcLayerParams& prm,
                            int num_sms, int* error_flag, cudaStream_t stream);
 
-// ---- tensor-core convolution, halo-patch variant (tc_conv_patch.cu): 64 -> 64 channels, taps within the
-//      3x3 neighbourhood (conv3/4, dconv5/6, dconv7's four phases) ------------------------------------
+// ---- tensor-core convolution, halo-patch variant (tc_conv_patch.cu): 64 or 32 -> 64 channels, taps within the
+//      3x3 neighbourhood (conv3/4, dconv5/6, the four phases of dconv7 and dconv1) ------------------------------------
 struct TcPatchStep {
   uint32_t a_off;      // byte offset of the tap's first pixel row inside the hi patch (tc_patch_a_offset)
   int16_t w_row;       // first row of this tap's [64 x 64] tile in the weight matrix
@@ -124,9 +124,9 @@ struct TcPatchParams {
   __half* out_lo;
   float* out_f32;
 };
-uint32_t tc_patch_a_offset(int dy, int dx);
-// a_hi / a_lo: plain activation views with box [64, 10, 1, 18, 1]
-cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes);
+// a_hi / a_lo: plain activation views with box [Cin, 10, 1, 18, 1]; row_bytes = 2*Cin (128 or 64)
+cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                  const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                  cudaStream_t stream);
 

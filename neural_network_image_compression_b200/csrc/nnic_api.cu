@@ -263,7 +263,7 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     }
     L.rows_per_set = 25 * sp.cout;
   }
-  L.use_patch = sp.cin == 64 && sp.cout == 64 && !(L.parity_view);
+  L.use_patch = sp.cout == 64 && !(L.parity_view);     // conv3/4, dconv5/6, dconv7 (Cin 64) and dconv1 (Cin 32)
   // Accumulation chains: the tensor core truncates its fp32 accumulator on every MMA, so long chains
   // drift (measured: ~50 ulp over 108 MMAs).  Each chain of <= ~12 k-steps gets its own TMEM slot and the
   // epilogue adds the chains with round-to-nearest fp32 adds.
@@ -521,8 +521,8 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
   TcLayer& L = h->tc[net][gi];
   if (L.use_patch && h->tc_patch && out_mode == TC_OUT_SPLIT) {
     CUtensorMap pa_hi, pa_lo;
-    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
-    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, false, 64, 128, 10, 18)) return rc;
+    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, false, L.kslab, L.row_bytes, 10, 18)) return rc;
+    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, false, L.kslab, L.row_bytes, 10, 18)) return rc;
     TcPatchParams pp;
     memset(&pp, 0, sizeof pp);
     pp.njobs = L.njobs;
@@ -533,7 +533,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       dst.chain_end_mask = 0;
       dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
       for (int s = 0; s < src.nsteps; ++s) {
-        dst.steps[s].a_off = tc_patch_a_offset(src.steps[s].dy, src.steps[s].dx);
+        dst.steps[s].a_off = tc_patch_a_offset(src.steps[s].dy, src.steps[s].dx, L.row_bytes);
         dst.steps[s].w_row = src.steps[s].w_row;
       }
     }
@@ -554,7 +554,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       pp.dbg_buf = prof_buf;
     }
     CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st,
-        launch_tc_conv_patch(pa_hi, pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
+        launch_tc_conv_patch(L.row_bytes, pa_hi, pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
     if (prof) {
       std::vector<long long> hb(148 * 4 * 8);
       cudaStreamSynchronize(st);

@@ -25,35 +25,49 @@ using namespace tc;
 constexpr int kThreads = 384;                 // warp 0 weight TMA, warps 1-2 MMA issuers, warps 3-10 epilogue, warp 11 patch TMA
 constexpr int kEpiWarp0 = 3;
 constexpr int kPatchWarp = 11;
+constexpr int NSPLIT = 2, kEpiWarps = 8;      // epilogue: 4 TMEM lane groups x 2 channel halves
 constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
-constexpr int PATCH_TX = PH * PW * 128;                      // bytes one patch load brings: 23040
-constexpr int PATCH_SLOT = (PATCH_TX + 1023) / 1024 * 1024;  // 23552
-constexpr int SET_BYTES = 2 * PATCH_SLOT;                    // hi + lo
 constexpr int NSETS = 2;
-constexpr int W_TILE = COUT * 128;                           // 8192: one of hi / lo
-constexpr int W_SLOT = 2 * W_TILE;                           // one tap: [W_hi | W_lo]
 constexpr int GTAPS = 3;                                     // taps per accumulation chain = per weight group
-constexpr int WG_BYTES = GTAPS * W_SLOT;                     // 32 KB
 constexpr int WSLOTS = 2;                                    // weight groups in flight
-constexpr int STG_WARP = 2048;                               // per-epilogue-warp staging buffer (32 pixels x 64 B)
-constexpr int STG_BYTES = 8 * STG_WARP;
 constexpr int SLOT_COLS = 2 * COUT, SLOTS = 4, TMEM_COLS = 512;
-constexpr int STG_OFF = NSETS * SET_BYTES + WSLOTS * WG_BYTES;
-constexpr int BAR_OFF = STG_OFF + STG_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * COUT * 4 + 1024;
-constexpr uint32_t A_SBO = PW * 128;
+
+// RB = bytes of one pixel row of the patch (64 input channels -> 128, SWIZZLE_128B; 32 -> 64, SWIZZLE_64B)
+template <int RB>
+struct PCfg {
+  static constexpr int KSTEPS = RB / 32;                                 // 16-element k-steps per tap
+  static constexpr int PATCH_TX = PH * PW * RB;                          // bytes one patch load brings
+  static constexpr int PATCH_SLOT = (PATCH_TX + 1023) / 1024 * 1024;
+  static constexpr int SET_BYTES = 2 * PATCH_SLOT;                       // hi + lo
+  static constexpr int W_TILE = COUT * RB;                               // one of hi / lo
+  static constexpr int W_SLOT = 2 * W_TILE;                              // one tap: [W_hi | W_lo]
+  static constexpr int WG_BYTES = GTAPS * W_SLOT;
+  static constexpr int STG_WARP = 32 * (COUT / NSPLIT) * 2;              // per-epilogue-warp staging: 32 pixels x HALF fp16
+  static constexpr int STG_BYTES = kEpiWarps * STG_WARP;
+  static constexpr int STG_OFF = NSETS * SET_BYTES + WSLOTS * WG_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * COUT * 4 + 1024;
+  static constexpr uint32_t A_SBO = PW * RB;                             // 8-row group stride of a tap view: one patch row
+  static constexpr uint64_t LAYOUT = RB == 128 ? 2ull : 4ull;            // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr uint32_t W_SBO = 8 * RB;
+};
 
 #define TICK() ((long long)clock64())                         // 8-row group stride of a tap view: one patch row
 
-__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint64_t layout) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
+template <int RB>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
+  using C = PCfg<RB>;
+  constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
+                WG_BYTES = C::WG_BYTES, STG_WARP = C::STG_WARP, STG_OFF = C::STG_OFF, BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
+  constexpr uint32_t A_SBO = C::A_SBO;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patch_base = smem;                                  // [NSETS][hi | lo]
@@ -68,7 +82,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 256);
   static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 256, "barrier area too small");
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -172,18 +186,18 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             mbar_wait(&w_full[ws], wphase, error_flag, 5); tw_w += TICK() - t1; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
-          const uint64_t w0 = make_desc_sbo(w_u32 + ws * WG_BYTES, 1024);   // tap k: + k*W_SLOT; W_hi followed by W_lo
+          const uint64_t w0 = make_desc_sbo(w_u32 + ws * WG_BYTES, C::W_SBO, C::LAYOUT);   // tap k: + k*W_SLOT; W_hi followed by W_lo
           const long long ti0 = TICK();
           if (elect_one()) {
             if (!(prm.dbg & 1)) {
 #pragma unroll
               for (int k = 0; k < GTAPS; ++k) {
                 if (k < ntaps) {
-                  const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO);
+                  const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO, C::LAYOUT);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
                   const uint64_t w_hl = w0 + (uint64_t)((k * W_SLOT) >> 4);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
+                  for (int ks = 0; ks < KSTEPS; ++ks) {
                     umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, (k | ks) ? 1u : 0u);
                     umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
                   }
@@ -346,14 +360,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 }  // namespace
 
-uint32_t tc_patch_a_offset(int dy, int dx) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * 128); }
+uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                                 const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
-                                 cudaStream_t stream) {
+template <int RB>
+static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                     const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
+                                     cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -361,8 +376,16 @@ cudaError_t launch_tc_conv_patch(const CUtensorMap& a_hi, const CUtensorMap& a_l
   const long long items = (long long)tiles_x * tiles_y * prm.P;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_conv_patch<<<grid, kThreads, SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
+  k_tc_conv_patch<RB><<<grid, kThreads, PCfg<RB>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
   return cudaGetLastError();
+}
+
+cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                 const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
+                                 cudaStream_t stream) {
+  if (row_bytes == 128) return launch_patch_impl<128>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 64) return launch_patch_impl<64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace nnic
