@@ -109,6 +109,11 @@ struct TcPatchJob {
 struct TcPatchParams {
   int njobs;
   TcPatchJob jobs[MAX_JOBS];
+  // activation patches per work item: 1, or 2 for conv2 (one per input-row parity; job 0's first seg_steps[0] steps
+  // read patch 0, the rest patch 1).  a_off bit 31 = the step only uses the upper half of its K slab.
+  int npatch;
+  int patch_py[2];
+  int seg_steps[2];
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;

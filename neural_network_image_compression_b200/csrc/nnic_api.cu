@@ -263,7 +263,8 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     }
     L.rows_per_set = 25 * sp.cout;
   }
-  L.use_patch = sp.cout == 64 && !(L.parity_view);     // conv3/4, dconv5/6, dconv7 (Cin 64) and dconv1 (Cin 32)
+  // conv3/4, dconv5/6, dconv7 (Cin 64), dconv1 (Cin 32), and conv2 (two patches, one per input-row parity)
+  L.use_patch = sp.cout == 64 && (!L.parity_view || sp.cin == 32);
   // Accumulation chains: the tensor core truncates its fp32 accumulator on every MMA, so long chains
   // drift (measured: ~50 ulp over 108 MMAs).  Each chain of <= ~12 k-steps gets its own TMEM slot and the
   // epilogue adds the chains with round-to-nearest fp32 adds.
@@ -521,11 +522,32 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
   TcLayer& L = h->tc[net][gi];
   if (L.use_patch && h->tc_patch && out_mode == TC_OUT_SPLIT) {
     CUtensorMap pa_hi, pa_lo;
-    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, false, L.kslab, L.row_bytes, 10, 18)) return rc;
-    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, false, L.kslab, L.row_bytes, 10, 18)) return rc;
+    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
+    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
     TcPatchParams pp;
     memset(&pp, 0, sizeof pp);
     pp.njobs = L.njobs;
+    pp.npatch = 1;
+    if (L.parity_view) {
+      // conv2: steps (kernel row a, column pair jj).  Rows a = 0,2,4 read input rows of parity 1 (patch 0), rows 1,3 parity 0
+      // (patch 1); both patches start one view row above the tile.  jj = -1 only uses the upper half of its K slab.
+      const TcJob& src = L.jobs[0];
+      TcPatchJob& dst = pp.jobs[0];
+      dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 2) / 3; dst.out_oy = 0; dst.out_ox = 0;
+      pp.npatch = 2; pp.patch_py[0] = 1; pp.patch_py[1] = 0;
+      int n = 0;
+      for (int seg = 0; seg < 2; ++seg) {
+        int cnt = 0;
+        for (int s = 0; s < src.nsteps; ++s) {
+          const TcStep& st2 = src.steps[s];
+          if (st2.py != pp.patch_py[seg]) continue;
+          dst.steps[n].a_off = tc_patch_a_offset(st2.dy, st2.dx, L.row_bytes) | (st2.ks_begin ? 0x80000000u : 0u);
+          dst.steps[n].w_row = st2.w_row;
+          ++n; ++cnt;
+        }
+        pp.seg_steps[seg] = cnt;
+      }
+    } else
     for (int j = 0; j < L.njobs; ++j) {
       const TcJob& src = L.jobs[j];
       TcPatchJob& dst = pp.jobs[j];

@@ -111,19 +111,21 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane, p = it / tiles_per_plane;
       const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
-      mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1);
-      if (elect_one()) {
-        uint8_t* pbuf = patch_base + pb * SET_BYTES;
-        if (prm.dbg & 16) {
-          mbar_arrive(&patch_full[pb]);
-        } else {
-          mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
-          tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
-          tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], 0, X0 - 1, 0, Y0 - 1, p);
+      for (int q = 0; q < prm.npatch; ++q) {
+        mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1);
+        if (elect_one()) {
+          uint8_t* pbuf = patch_base + pb * SET_BYTES;
+          if (prm.dbg & 16) {
+            mbar_arrive(&patch_full[pb]);
+          } else {
+            mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
+            tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], 0, X0 - 1, prm.patch_py[q], Y0 - 1, p);
+            tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], 0, X0 - 1, prm.patch_py[q], Y0 - 1, p);
+          }
         }
+        __syncwarp();
+        if (++pb == NSETS) { pb = 0; pphase ^= 1; }
       }
-      __syncwarp();
-      if (++pb == NSETS) { pb = 0; pphase ^= 1; }
     }
   } else if (warp == 0) {
     // ===================== TMA producer: weight groups =====================
@@ -168,12 +170,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int ws = 0; uint32_t wphase = 0;
     int slot = 0; uint32_t slot_phase = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      for (int seg = 0; seg < prm.npatch; ++seg) {
       { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, error_flag, 3); tw_patch += TICK() - t0; }
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
-      for (int j = 0; j < prm.njobs; ++j) {
-        const int nsteps = prm.jobs[j].nsteps;
-        for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
-          const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
+      const int njobs_seg = prm.npatch == 1 ? prm.njobs : 1;
+      for (int j = 0; j < njobs_seg; ++j) {
+        const int sbeg = prm.npatch == 1 ? 0 : (seg == 0 ? 0 : prm.seg_steps[0]);
+        const int send = prm.npatch == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
+        for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
+          const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
           if (((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
             if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
@@ -190,16 +195,21 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           const long long ti0 = TICK();
           if (elect_one()) {
             if (!(prm.dbg & 1)) {
+              uint32_t accumulate = 0u;
 #pragma unroll
               for (int k = 0; k < GTAPS; ++k) {
                 if (k < ntaps) {
-                  const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO, C::LAYOUT);
+                  const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
                   const uint64_t w_hl = w0 + (uint64_t)((k * W_SLOT) >> 4);
+                  const int ks_begin = (a_off[k] >> 31) ? KSTEPS / 2 : 0;
 #pragma unroll
                   for (int ks = 0; ks < KSTEPS; ++ks) {
-                    umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, (k | ks) ? 1u : 0u);
-                    umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                    if (ks >= ks_begin) {
+                      umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, accumulate);
+                      umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                      accumulate = 1u;
+                    }
                   }
                 }
               }
@@ -213,9 +223,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
         }
       }
-      if (elect_one()) umma_commit(&patch_empty[pb]);      // every MMA of this work item has read the patch
+      if (elect_one()) umma_commit(&patch_empty[pb]);      // every MMA of this segment has read the patch
       __syncwarp();
       if (++pb == NSETS) { pb = 0; pphase ^= 1; }
+      }
     }
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
   } else {
