@@ -53,7 +53,12 @@ struct PCfg {
   static constexpr uint32_t W_SBO = 8 * RB;
 };
 
-#define TICK() ((long long)clock64())                         // 8-row group stride of a tap view: one patch row
+// role timers (profiles/r1_tcprof_*.log) are compiled in with -DNNIC_TC_TIMERS; they cost a few hundred cycles per tile
+#ifdef NNIC_TC_TIMERS
+#define TICK() ((long long)clock64())
+#else
+#define TICK() 0LL
+#endif                         // 8-row group stride of a tap view: one patch row
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint64_t layout) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
