@@ -22,9 +22,10 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 384;                 // warp 0 weight TMA, warps 1-2 MMA issuers, warps 3-10 epilogue, warp 11 patch TMA
-constexpr int kEpiWarp0 = 3;
-constexpr int kPatchWarp = 11;
+constexpr int kNumMma = 2;                     // MMA issuer warps (2 = alternate chains)
+constexpr int kEpiWarp0 = 1 + kNumMma;
+constexpr int kPatchWarp = kEpiWarp0 + 8;
+constexpr int kThreads = (kPatchWarp + 1) * 32;   // warp 0 weight TMA, MMA issuer(s), 8 epilogue warps, last warp patch TMA
 constexpr int NSPLIT = 2, kEpiWarps = 8;      // epilogue: 4 TMEM lane groups x 2 channel halves
 constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
@@ -92,7 +93,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 2); }
+    for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kNumMma); }
     for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,7 +185,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int send = prm.npatch == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
         for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
           const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
-          if (((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
+          if (kNumMma == 2 && ((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
             if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
             continue;
