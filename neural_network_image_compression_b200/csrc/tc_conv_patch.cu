@@ -23,10 +23,7 @@ namespace {
 using namespace tc;
 
 constexpr int kNumMma = 2;                     // MMA issuer warps (2 = alternate chains)
-constexpr int kEpiWarp0 = 1 + kNumMma;
-constexpr int kPatchWarp = kEpiWarp0 + 8;
-constexpr int kThreads = (kPatchWarp + 1) * 32;   // warp 0 weight TMA, MMA issuer(s), 8 epilogue warps, last warp patch TMA
-constexpr int NSPLIT = 2, kEpiWarps = 8;      // epilogue: 4 TMEM lane groups x 2 channel halves
+constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s), 4*NSPLIT epilogue warps, last warp patch TMA
 constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
@@ -35,8 +32,11 @@ constexpr int WSLOTS = 2;                                    // weight groups in
 constexpr int SLOT_COLS = 2 * COUT, SLOTS = 4, TMEM_COLS = 512;
 
 // RB = bytes of one pixel row of the patch (64 input channels -> 128, SWIZZLE_128B; 32 -> 64, SWIZZLE_64B)
-template <int RB>
+template <int RB, int NSPLIT>
 struct PCfg {
+  static constexpr int kEpiWarps = 4 * NSPLIT;                          // NSPLIT warps per TMEM lane group, COUT/NSPLIT channels each
+  static constexpr int kPatchWarp = kEpiWarp0 + kEpiWarps;
+  static constexpr int kThreads = (kPatchWarp + 1) * 32;
   static constexpr int KSTEPS = RB / 32;                                 // 16-element k-steps per tap
   static constexpr int PATCH_TX = PH * PW * RB;                          // bytes one patch load brings
   static constexpr int PATCH_SLOT = (PATCH_TX + 1023) / 1024 * 1024;
@@ -65,12 +65,13 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int RB>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int RB, int NSPLIT>
+__global__ void __launch_bounds__((PCfg<RB, NSPLIT>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
-  using C = PCfg<RB>;
+  using C = PCfg<RB, NSPLIT>;
+  constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
                 WG_BYTES = C::WG_BYTES, STG_WARP = C::STG_WARP, STG_OFF = C::STG_OFF, BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
   constexpr uint32_t A_SBO = C::A_SBO;
@@ -95,7 +96,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kNumMma); }
     for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 8); }
+    for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -237,51 +238,53 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
   } else {
     // ===================== epilogue warps =====================
-    constexpr int HALF = COUT / 2;
+    constexpr int HALF = COUT / NSPLIT;       // channels per thread
+    constexpr int PP = HALF / 8;              // 16-byte pieces per pixel (per hi / lo plane)
+    constexpr int PIX_PER_INSTR = 32 / PP;    // pixels one coalesced instruction covers
+    constexpr int NINSTR = 32 / PIX_PER_INSTR;
     const int lg = warp & 3;
     const int hf = (warp - kEpiWarp0) >> 2;
-    const int m = lg * 32 + lane;
-    const int r = m >> 3, c = m & 7;
     const int ch0 = hf * HALF;
     int slot = 0; uint32_t slot_phase = 0;
     long long tw_full = 0, t_ld = 0, t_out = 0, t_begin = TICK();
+    uint4* stg4 = reinterpret_cast<uint4*>(smem + STG_OFF + (warp - kEpiWarp0) * STG_WARP);
+    // staging index (16-byte units) of piece j of pixel-lane i; conflict-free for own-row and grouped access
+    auto sidx = [](int i, int j) { return PP == 4 ? i * 4 + ((j ^ (i >> 1)) & 3) : i * 2 + ((j ^ (i >> 2)) & 1); };
+    const int gpiece = lane % PP, gpix = lane / PP;        // this lane's piece / pixel inside a coalesced instruction
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane;
       const int p = it / tiles_per_plane;
-      const int Y = (txy / tiles_x) * kTileRows + r, X = (txy % tiles_x) * kTileCols + c;
+      const int tY0 = (txy / tiles_x) * kTileRows, tX0 = (txy % tiles_x) * kTileCols;
       const int set = p < prm.n_split ? 0 : 1;
       const float inv_scale = prm.inv_scale[set];
       const float* bs = bias_s + set * COUT + ch0;
       for (int j = 0; j < prm.njobs; ++j) {
         const int nchains = prm.jobs[j].nchains;
-        const int oy = Y * prm.out_stride + prm.jobs[j].out_oy, ox = X * prm.out_stride + prm.jobs[j].out_ox;
-        const bool valid = Y < prm.Hp && X < prm.Wp && oy < prm.Ho && ox < prm.Wo;
         float acc[HALF];
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.0f;
-        // Global accesses of the epilogue are re-mapped through a per-warp staging buffer so that one
-        // instruction touches eight 64-byte runs (full sectors): lane l handles 16-byte piece (l & 3) of the
-        // pixel in tile row (4*lg + R), column (l >> 2), for R = 0..3.
-        uint8_t* stg = smem + STG_OFF + (warp - kEpiWarp0) * STG_WARP;
-        const int gcol = lane >> 2, gpiece = lane & 3;
-        size_t goff[4];                     // element offset of this lane's piece for R = 0..3, or ~0 when outside
+        // Global accesses of the epilogue are re-mapped through a per-warp staging buffer so that one instruction
+        // touches full 32-byte sectors: in instruction i, lane l handles 16-byte piece (l % PP) of the pixel
+        // i*PIX_PER_INSTR + l/PP of this warp's 32 pixels (4 tile rows x 8 columns).
+        size_t goff[NINSTR];                // element offset of this lane's piece, or ~0 when outside the image
 #pragma unroll
-        for (int R = 0; R < 4; ++R) {
-          const int gY = (txy / tiles_x) * kTileRows + lg * 4 + R, gX = (txy % tiles_x) * kTileCols + gcol;
+        for (int i = 0; i < NINSTR; ++i) {
+          const int q = i * PIX_PER_INSTR + gpix;
+          const int gY = tY0 + lg * 4 + (q >> 3), gX = tX0 + (q & 7);
           const int goy = gY * prm.out_stride + prm.jobs[j].out_oy, gox = gX * prm.out_stride + prm.jobs[j].out_ox;
           const bool gvalid = gY < prm.Hp && gX < prm.Wp && goy < prm.Ho && gox < prm.Wo;
-          goff[R] = gvalid ? (((size_t)p * prm.Ho + goy) * prm.Wo + gox) * COUT + ch0 + gpiece * 8 : ~(size_t)0;
+          goff[i] = gvalid ? (((size_t)p * prm.Ho + goy) * prm.Wo + gox) * COUT + ch0 + gpiece * 8 : ~(size_t)0;
         }
         // residual: coalesced loads now (latency hides behind the MMAs), redistributed to the owning lanes later
-        uint4 res_h[4], res_l[4];
+        uint4 res_h[NINSTR], res_l[NINSTR];
         const bool has_res = prm.res_hi != nullptr;
         if (has_res) {
 #pragma unroll
-          for (int R = 0; R < 4; ++R) {
-            res_h[R] = make_uint4(0, 0, 0, 0); res_l[R] = make_uint4(0, 0, 0, 0);
-            if (goff[R] != ~(size_t)0) {
-              res_h[R] = *reinterpret_cast<const uint4*>(prm.res_hi + goff[R]);
-              res_l[R] = *reinterpret_cast<const uint4*>(prm.res_lo + goff[R]);
+          for (int i = 0; i < NINSTR; ++i) {
+            res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
+            if (goff[i] != ~(size_t)0) {
+              res_h[i] = *reinterpret_cast<const uint4*>(prm.res_hi + goff[i]);
+              res_l[i] = *reinterpret_cast<const uint4*>(prm.res_lo + goff[i]);
             }
           }
         }
@@ -292,74 +295,61 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
           uint32_t vm[HALF], vc[HALF];
-          if (prm.dbg & 8) {
-#pragma unroll
-            for (int i = 0; i < HALF; ++i) { vm[i] = 0; vc[i] = 0; }
-          } else {
-            tmem_ld32_nowait(taddr, vm);
-            tmem_ld32_nowait(taddr + COUT, vc);
-            tmem_ld_wait();
-          }
+          if (HALF == 32) { tmem_ld32_nowait(taddr, vm); tmem_ld32_nowait(taddr + COUT, vc); }
+          else { tmem_ld16_nowait(taddr, vm); tmem_ld16_nowait(taddr + COUT, vc); }
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_empty[slot]);
-          if (!(prm.dbg & 32)) {
 #pragma unroll
-            for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
-          }
+          for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
           t_ld += TICK() - te1;
         }
         const long long to0 = TICK();
-        if (!(prm.dbg & 2)) {
-          // piece j of lane i lives at i*64 + ((j ^ (i >> 1)) & 3)*16: conflict-free for both access patterns
-          auto stg_own = [&](int j) { return reinterpret_cast<uint4*>(stg + lane * 64 + (((j ^ (lane >> 1)) & 3) << 4)); };
-          auto stg_grp = [&](int R) { const int q = R * 8 + gcol; return reinterpret_cast<uint4*>(stg + q * 64 + (((gpiece ^ (q >> 1)) & 3) << 4)); };
-          float rsum[HALF];
+        {
+          // bias + leaky_relu in place (x*2^-k is exact, so the fused multiply-add rounds exactly like mul then add)
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) {
+            const float v = fmaf(acc[i], inv_scale, bs[i]);
+            acc[i] = fmaxf(v, __fmul_rn(v, LEAKY_ALPHA));
+          }
           if (has_res) {
-            // hi pieces -> owners, then lo pieces -> owners
-            uint4 own_h[4], own_l[4];
+            uint4 own_h[PP], own_l[PP];
 #pragma unroll
-            for (int R = 0; R < 4; ++R) *stg_grp(R) = res_h[R];
+            for (int i = 0; i < NINSTR; ++i) stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)] = res_h[i];
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) own_h[q] = *stg_own(q);
+            for (int q = 0; q < PP; ++q) own_h[q] = stg4[sidx(lane, q)];
             __syncwarp();
 #pragma unroll
-            for (int R = 0; R < 4; ++R) *stg_grp(R) = res_l[R];
+            for (int i = 0; i < NINSTR; ++i) stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)] = res_l[i];
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) own_l[q] = *stg_own(q);
+            for (int q = 0; q < PP; ++q) own_l[q] = stg4[sidx(lane, q)];
             __syncwarp();
             const __half* rh = reinterpret_cast<const __half*>(own_h);
             const __half* rl = reinterpret_cast<const __half*>(own_l);
 #pragma unroll
-            for (int i = 0; i < HALF; ++i) rsum[i] = join_f32(rh[i], rl[i]);
+            for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], join_f32(rh[i], rl[i]));
           }
           __align__(16) uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-          for (int i = 0; i < HALF; i += 2) {
-            float v0 = leaky(__fadd_rn(acc[i] * inv_scale, bs[i]));
-            float v1 = leaky(__fadd_rn(acc[i + 1] * inv_scale, bs[i + 1]));
-            if (has_res) { v0 = __fadd_rn(v0, rsum[i]); v1 = __fadd_rn(v1, rsum[i + 1]); }
-            split2_f32(v0, v1, h[i / 2], l[i / 2]);
-          }
-          if (prm.out_mode == TC_OUT_SPLIT) {
+          for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *stg_own(q) = reinterpret_cast<uint4*>(h)[q];
-            __syncwarp();
+          for (int q = 0; q < PP; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(h)[q];
+          __syncwarp();
 #pragma unroll
-            for (int R = 0; R < 4; ++R)
-              if (goff[R] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_hi + goff[R]) = *stg_grp(R);
-            __syncwarp();
+          for (int i = 0; i < NINSTR; ++i)
+            if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_hi + goff[i]) = stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)];
+          __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *stg_own(q) = reinterpret_cast<uint4*>(l)[q];
-            __syncwarp();
+          for (int q = 0; q < PP; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(l)[q];
+          __syncwarp();
 #pragma unroll
-            for (int R = 0; R < 4; ++R)
-              if (goff[R] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_lo + goff[R]) = *stg_grp(R);
-            __syncwarp();
-          }
+          for (int i = 0; i < NINSTR; ++i)
+            if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_lo + goff[i]) = stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)];
+          __syncwarp();
         }
         t_out += TICK() - to0;
       }
@@ -379,13 +369,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB>
+template <int RB, int NSPLIT>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -393,15 +383,18 @@ static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap&
   const long long items = (long long)tiles_x * tiles_y * prm.P;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_conv_patch<RB><<<grid, kThreads, PCfg<RB>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
+  k_tc_conv_patch<RB, NSPLIT><<<grid, PCfg<RB, NSPLIT>::kThreads, PCfg<RB, NSPLIT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
   return cudaGetLastError();
 }
 
 cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                  const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                  cudaStream_t stream) {
-  if (row_bytes == 128) return launch_patch_impl<128>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
-  if (row_bytes == 64) return launch_patch_impl<64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  // layers whose epilogue is the limiter (residual add, or several output phases per work item) use 16 epilogue warps
+  const bool heavy_epilogue = prm.res_hi != nullptr || prm.njobs > 1;
+  if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 128) return launch_patch_impl<128, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 64) return launch_patch_impl<64, 4>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   return cudaErrorInvalidValue;
 }
 
