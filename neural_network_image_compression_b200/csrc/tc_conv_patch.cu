@@ -239,18 +239,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else {
     // ===================== epilogue warps =====================
     constexpr int HALF = COUT / NSPLIT;       // channels per thread
-    constexpr int PP = HALF / 8;              // 16-byte pieces per pixel (per hi / lo plane)
-    constexpr int PIX_PER_INSTR = 32 / PP;    // pixels one coalesced instruction covers
-    constexpr int NINSTR = 32 / PIX_PER_INSTR;
     const int lg = warp & 3;
     const int hf = (warp - kEpiWarp0) >> 2;
     const int ch0 = hf * HALF;
     int slot = 0; uint32_t slot_phase = 0;
     long long tw_full = 0, t_ld = 0, t_out = 0, t_begin = TICK();
-    uint4* stg4 = reinterpret_cast<uint4*>(smem + STG_OFF + (warp - kEpiWarp0) * STG_WARP);
-    // staging index (16-byte units) of piece j of pixel-lane i; conflict-free for own-row and grouped access
-    auto sidx = [](int i, int j) { return PP == 4 ? i * 4 + ((j ^ (i >> 1)) & 3) : i * 2 + ((j ^ (i >> 2)) & 1); };
-    const int gpiece = lane % PP, gpix = lane / PP;        // this lane's piece / pixel inside a coalesced instruction
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane;
       const int p = it / tiles_per_plane;
@@ -263,28 +256,24 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         float acc[HALF];
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.0f;
-        // Global accesses of the epilogue are re-mapped through a per-warp staging buffer so that one instruction
-        // touches full 32-byte sectors: in instruction i, lane l handles 16-byte piece (l % PP) of the pixel
-        // i*PIX_PER_INSTR + l/PP of this warp's 32 pixels (4 tile rows x 8 columns).
-        size_t goff[NINSTR];                // element offset of this lane's piece, or ~0 when outside the image
-#pragma unroll
-        for (int i = 0; i < NINSTR; ++i) {
-          const int q = i * PIX_PER_INSTR + gpix;
-          const int gY = tY0 + lg * 4 + (q >> 3), gX = tX0 + (q & 7);
-          const int goy = gY * prm.out_stride + prm.jobs[j].out_oy, gox = gX * prm.out_stride + prm.jobs[j].out_ox;
-          const bool gvalid = gY < prm.Hp && gX < prm.Wp && goy < prm.Ho && gox < prm.Wo;
-          goff[i] = gvalid ? (((size_t)p * prm.Ho + goy) * prm.Wo + gox) * COUT + ch0 + gpiece * 8 : ~(size_t)0;
-        }
-        // residual: coalesced loads now (latency hides behind the MMAs), redistributed to the owning lanes later
-        uint4 res_h[NINSTR], res_l[NINSTR];
+        // every thread owns HALF consecutive channels of one pixel: 2*HALF bytes per fp16 plane, moved with 256-bit
+        // accesses (one full 32-byte sector per thread and instruction)
+        const int oY = tY0 + lg * 4 + (lane >> 3), oX = tX0 + (lane & 7);
+        const int ooy = oY * prm.out_stride + prm.jobs[j].out_oy, oox = oX * prm.out_stride + prm.jobs[j].out_ox;
+        const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo;
+        const size_t ooff = (((size_t)p * prm.Ho + ooy) * prm.Wo + oox) * COUT + ch0;
+        // residual: loaded now so that its latency hides behind the MMAs
+        uint32_t res_h[HALF / 2], res_l[HALF / 2];
         const bool has_res = prm.res_hi != nullptr;
         if (has_res) {
 #pragma unroll
-          for (int i = 0; i < NINSTR; ++i) {
-            res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
-            if (goff[i] != ~(size_t)0) {
-              res_h[i] = *reinterpret_cast<const uint4*>(prm.res_hi + goff[i]);
-              res_l[i] = *reinterpret_cast<const uint4*>(prm.res_lo + goff[i]);
+          for (int q = 0; q < HALF / 16; ++q) {
+            if (valid) {
+              ld_global_v8(prm.res_hi + ooff + 16 * q, res_h + 8 * q);
+              ld_global_v8(prm.res_lo + ooff + 16 * q, res_l + 8 * q);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { res_h[8 * q + e] = 0; res_l[8 * q + e] = 0; }
             }
           }
         }
@@ -315,41 +304,21 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             acc[i] = fmaxf(v, __fmul_rn(v, LEAKY_ALPHA));
           }
           if (has_res) {
-            uint4 own_h[PP], own_l[PP];
-#pragma unroll
-            for (int i = 0; i < NINSTR; ++i) stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)] = res_h[i];
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < PP; ++q) own_h[q] = stg4[sidx(lane, q)];
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NINSTR; ++i) stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)] = res_l[i];
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < PP; ++q) own_l[q] = stg4[sidx(lane, q)];
-            __syncwarp();
-            const __half* rh = reinterpret_cast<const __half*>(own_h);
-            const __half* rl = reinterpret_cast<const __half*>(own_l);
+            const __half* rh = reinterpret_cast<const __half*>(res_h);
+            const __half* rl = reinterpret_cast<const __half*>(res_l);
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], join_f32(rh[i], rl[i]));
           }
-          __align__(16) uint32_t h[HALF / 2], l[HALF / 2];
+          uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
           for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
+          if (valid) {
 #pragma unroll
-          for (int q = 0; q < PP; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(h)[q];
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < NINSTR; ++i)
-            if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_hi + goff[i]) = stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)];
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < PP; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(l)[q];
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < NINSTR; ++i)
-            if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_lo + goff[i]) = stg4[sidx(i * PIX_PER_INSTR + gpix, gpiece)];
-          __syncwarp();
+            for (int q = 0; q < HALF / 16; ++q) {
+              st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
+              st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
+            }
+          }
         }
         t_out += TICK() - to0;
       }
