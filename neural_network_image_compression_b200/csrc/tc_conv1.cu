@@ -211,10 +211,6 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     const int lg = warp & 3;                  // TMEM lane group
     const int hf = ew >> 2;
     const int ch0 = hf * HALF;
-    uint4* stg4 = reinterpret_cast<uint4*>(smem + STG_OFF + ew * STG_WARP);
-    // staging index (16-byte units) of piece j (of 2) of pixel-lane i; conflict-free for both access patterns
-    auto sidx = [](int i, int j) { return i * 2 + ((j ^ (i >> 2)) & 1); };
-    const int gpiece = lane & 1, gpix = lane >> 1;
     int slot = 0; uint32_t slot_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int txy = t % tiles_per_plane, p = t / tiles_per_plane;
@@ -240,28 +236,14 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         const float v1 = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i + 1]), __uint_as_float(vc[i + 1])) * inv_scale, bs[i + 1]));
         split2_f32(v0, v1, h[i / 2], l[i / 2]);
       }
-      // in instruction i, lane l stores 16-byte piece (l & 1) of pixel i*16 + (l >> 1) of this warp's 32 pixels
-      size_t goff[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int q = i * 16 + gpix;
-        const int y = tY0 + lg * 4 + (q >> 3), x = tX0 + (q & 7);
-        goff[i] = (y < Ho && x < Wo) ? (((size_t)p * Ho + y) * Wo + x) * CO + ch0 + gpiece * 8 : ~(size_t)0;
+      // 16 channels = 32 bytes per fp16 plane: one 256-bit store each (a full sector per thread)
+      const int m = lg * 32 + lane;
+      const int y = tY0 + (m >> 3), x = tX0 + (m & 7);
+      if (y < Ho && x < Wo) {
+        const size_t o = (((size_t)p * Ho + y) * Wo + x) * CO + ch0;
+        st_global_v8(prm.out_hi + o, h);
+        st_global_v8(prm.out_lo + o, l);
       }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(h)[q];
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_hi + goff[i]) = stg4[sidx(i * 16 + gpix, gpiece)];
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) stg4[sidx(lane, q)] = reinterpret_cast<uint4*>(l)[q];
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (goff[i] != ~(size_t)0) *reinterpret_cast<uint4*>(prm.out_lo + goff[i]) = stg4[sidx(i * 16 + gpix, gpiece)];
-      __syncwarp();
     }
   }
 
