@@ -211,29 +211,40 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     const int lg = warp & 3;                  // TMEM lane group
     const int hf = ew >> 2;
     const int ch0 = hf * HALF;
+    // Software-pipelined: the TMEM loads of tile t+1 are issued before the arithmetic of tile t, so the TMEM
+    // and barrier latencies overlap the bias / leaky / split / store work instead of adding to it.
     int slot = 0; uint32_t slot_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int txy = t % tiles_per_plane, p = t / tiles_per_plane;
-      const int set = p < N ? 0 : 1;
-      const int tY0 = (txy / tiles_x) * kTileRows, tX0 = (txy % tiles_x) * kTileCols;
+    uint32_t cm[HALF], cc_[HALF], nm[HALF], nc[HALF];
+    auto issue_loads = [&](uint32_t* vm, uint32_t* vc) {
       mbar_wait(&slot_full[slot], slot_phase, error_flag, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
-      uint32_t vm[HALF], vc[HALF];
       tmem_ld16_nowait(taddr, vm);
       tmem_ld16_nowait(taddr + CO, vc);
+    };
+    auto release_slot = [&]() {
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&slot_empty[slot]);
       if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+    };
+    if ((int)blockIdx.x < num_tiles) { issue_loads(cm, cc_); release_slot(); }
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int txy = t % tiles_per_plane, p = t / tiles_per_plane;
+      const int set = p < N ? 0 : 1;
+      const int tY0 = (txy / tiles_x) * kTileRows, tX0 = (txy % tiles_x) * kTileCols;
+      const bool has_next = t + (int)gridDim.x < num_tiles;
+      if (has_next) issue_loads(nm, nc);
       const float inv_scale = prm.inv_scale[set];
       const float* bs = bias_s + set * CO + ch0;
-      __align__(16) uint32_t h[HALF / 2], l[HALF / 2];
+      uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
       for (int i = 0; i < HALF; i += 2) {
-        const float v0 = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])) * inv_scale, bs[i]));
-        const float v1 = leaky(__fadd_rn(__fadd_rn(__uint_as_float(vm[i + 1]), __uint_as_float(vc[i + 1])) * inv_scale, bs[i + 1]));
+        float v0 = fmaf(__fadd_rn(__uint_as_float(cm[i]), __uint_as_float(cc_[i])), inv_scale, bs[i]);
+        float v1 = fmaf(__fadd_rn(__uint_as_float(cm[i + 1]), __uint_as_float(cc_[i + 1])), inv_scale, bs[i + 1]);
+        v0 = fmaxf(v0, __fmul_rn(v0, LEAKY_ALPHA));
+        v1 = fmaxf(v1, __fmul_rn(v1, LEAKY_ALPHA));
         split2_f32(v0, v1, h[i / 2], l[i / 2]);
       }
       // 16 channels = 32 bytes per fp16 plane: one 256-bit store each (a full sector per thread)
@@ -243,6 +254,11 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         const size_t o = (((size_t)p * Ho + y) * Wo + x) * CO + ch0;
         st_global_v8(prm.out_hi + o, h);
         st_global_v8(prm.out_lo + o, l);
+      }
+      if (has_next) {
+        release_slot();
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) { cm[i] = nm[i]; cc_[i] = nc[i]; }
       }
     }
   }
