@@ -65,33 +65,8 @@ cudaError_t launch_entropy_u32(const uint32_t* hist, int N, float symbols_per_pl
 cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float* entropy,
                                cudaStream_t stream);
 
-// ---- tensor-core convolution (tc_conv.cu) -------------------------------------------------------
+// ---- tensor-core convolutions ------------------------------------------------------------------------
 enum TcOutMode { TC_OUT_SPLIT = 0, TC_OUT_F32 = 1, TC_OUT_QUANT = 2 };
-
-struct TcLayerParams {
-  int njobs;
-  TcJob jobs[MAX_JOBS];
-  int P, n_split;
-  int Hp, Wp;                 // phase grid (output pixels per phase)
-  int Ho, Wo, out_stride;     // output tensor geometry [P,Ho,Wo,COUT]; pixel = (Y*out_stride+oy, X*out_stride+ox)
-  int rows_per_set;           // rows of the weight matrix per weight set
-  float inv_scale[2];         // 2^-(ka+kw) per weight set
-  const float* bias;          // [2][COUT]
-  const __half* res_hi;       // optional residual, split fp16 [P,Ho,Wo,COUT]
-  const __half* res_lo;
-  int out_mode;
-  int clamp01;                // clip the activation to [0,1] (conv8: encoder.py:32)
-  __half* out_hi;             // TC_OUT_SPLIT
-  __half* out_lo;
-  float* out_f32;             // TC_OUT_F32: [P,Ho,Wo,COUT]
-  uint8_t* out_u8;            // TC_OUT_QUANT: latent [N,Ho,Wo,96] (COUT == 32), N = P/3
-  float* out_prequant;        // TC_OUT_QUANT, optional: f32 [N,Ho,Wo,96]
-};
-
-// row_bytes = bytes of one A row (64 or 128); cout = 32 or 64.
-cudaError_t launch_tc_conv(int row_bytes, int cout, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
-                           const CUtensorMap& w_hi, const CUtensorMap& w_lo, const TcLayerParams& prm,
-                           int num_sms, int* error_flag, cudaStream_t stream);
 
 // ---- tensor-core convolution, halo-patch variant (tc_conv_patch.cu): 64 or 32 -> 64 channels, taps within the
 //      3x3 neighbourhood (conv3/4, dconv5/6, the four phases of dconv7 and dconv1) ------------------------------------
@@ -111,9 +86,12 @@ struct TcPatchParams {
   TcPatchJob jobs[MAX_JOBS];
   // activation patches per work item: 1, or 2 for conv2 (one per input-row parity; job 0's first seg_steps[0] steps
   // read patch 0, the rest patch 1).  a_off bit 31 = the step only uses the upper half of its K slab.
+  // conv8 uses four (row parity, column parity) patches; patch_c0 = first element of the view's inner dimension.
   int npatch;
-  int patch_py[2];
-  int seg_steps[2];
+  int patch_py[4];
+  int patch_c0[4];
+  int seg_steps[4];
+  int cout;                   // 64, or 32 (conv8)
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;
@@ -122,7 +100,10 @@ struct TcPatchParams {
   const float* bias;
   const __half* res_hi;
   const __half* res_lo;
-  int out_mode;               // TC_OUT_SPLIT or TC_OUT_F32
+  int out_mode;               // TC_OUT_SPLIT; cout == 32 also TC_OUT_F32 / TC_OUT_QUANT
+  int clamp01;                // clip the activation to [0,1] (conv8: encoder.py:32)
+  uint8_t* out_u8;            // TC_OUT_QUANT: latent [N,Ho,Wo,96], N = P/3
+  float* out_prequant;        // TC_OUT_QUANT, optional: f32 [N,Ho,Wo,96]
   long long* dbg_buf;         // development: per-CTA role timers [grid][4][8] (NNIC_TC_PROF)
   int dbg;                    // development switches (NNIC_TC_DBG): 1 skip MMAs, 2 skip stores, 4 skip W loads, 8 skip TMEM loads
   __half* out_hi;

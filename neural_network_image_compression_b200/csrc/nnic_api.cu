@@ -54,7 +54,6 @@ struct TcLayer {
   float* bias = nullptr;       // [2][cout]
   CUtensorMap map_w_hi, map_w_lo;
   bool parity_view = false;    // input read through the [2C, W/2, 2, H/2, P] view (stride-2 convs)
-  bool use_patch = false;      // all taps within the 3x3 neighbourhood, 64 -> 64: halo-patch kernel
   int out_stride = 1;
 };
 struct SimtLayer {
@@ -72,7 +71,6 @@ struct nnic_handle {
   uint64_t launches = 0;
   int micro_batch = 0;
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
-  bool tc_patch = true;             // use the halo-patch kernel where it applies (NNIC_TC_PATCH=0 disables)
   EncodeTiledFn encode_tiled = nullptr;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
   int* error_flag_dev = nullptr;
@@ -263,8 +261,6 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     }
     L.rows_per_set = 25 * sp.cout;
   }
-  // conv3/4, dconv5/6, dconv7 (Cin 64), dconv1 (Cin 32), and conv2 (two patches, one per input-row parity)
-  L.use_patch = sp.cout == 64 && (!L.parity_view || sp.cin == 32);
   // Accumulation chains: the tensor core truncates its fp32 accumulator on every MMA, so long chains
   // drift (measured: ~50 ulp over 108 MMAs).  Each chain of <= ~12 k-steps gets its own TMEM slot and the
   // epilogue adds the chains with round-to-nearest fp32 adds.
@@ -520,7 +516,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     return 0;
   }
   TcLayer& L = h->tc[net][gi];
-  if (L.use_patch && h->tc_patch && out_mode == TC_OUT_SPLIT) {
+  {
     CUtensorMap pa_hi, pa_lo;
     if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
     if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
@@ -529,23 +525,27 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.njobs = L.njobs;
     pp.npatch = 1;
     if (L.parity_view) {
-      // conv2: steps (kernel row a, column pair jj).  Rows a = 0,2,4 read input rows of parity 1 (patch 0), rows 1,3 parity 0
-      // (patch 1); both patches start one view row above the tile.  jj = -1 only uses the upper half of its K slab.
+      // stride-2 convolutions read one patch per (input-row parity, inner offset) of the parity view; every patch starts one
+      // view row above the tile.  conv2: steps (kernel row a, column pair jj), rows a = 0,2,4 read row parity 1, rows 1,3
+      // parity 0; jj = -1 only uses the upper half of its K slab.  conv8: (row parity, column parity) = four patches.
       const TcJob& src = L.jobs[0];
       TcPatchJob& dst = pp.jobs[0];
-      dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 2) / 3; dst.out_oy = 0; dst.out_ox = 0;
-      pp.npatch = 2; pp.patch_py[0] = 1; pp.patch_py[1] = 0;
+      dst.nsteps = src.nsteps; dst.nchains = 0; dst.out_oy = 0; dst.out_ox = 0;
+      pp.npatch = 0;
       int n = 0;
-      for (int seg = 0; seg < 2; ++seg) {
+      for (int py = 1; py >= 0; --py) for (int c0 = 64; c0 >= 0; c0 -= 64) {
         int cnt = 0;
         for (int s = 0; s < src.nsteps; ++s) {
           const TcStep& st2 = src.steps[s];
-          if (st2.py != pp.patch_py[seg]) continue;
+          if (st2.py != py || st2.koff != c0) continue;
           dst.steps[n].a_off = tc_patch_a_offset(st2.dy, st2.dx, L.row_bytes) | (st2.ks_begin ? 0x80000000u : 0u);
           dst.steps[n].w_row = st2.w_row;
           ++n; ++cnt;
         }
-        pp.seg_steps[seg] = cnt;
+        if (!cnt) continue;
+        pp.patch_py[pp.npatch] = py; pp.patch_c0[pp.npatch] = c0; pp.seg_steps[pp.npatch] = cnt;
+        ++pp.npatch;
+        dst.nchains += (cnt + 2) / 3;              // chains do not span patches
       }
     } else
     for (int j = 0; j < L.njobs; ++j) {
@@ -565,6 +565,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.bias = L.bias;
     pp.res_hi = res ? res->hi : nullptr; pp.res_lo = res ? res->lo : nullptr;
     pp.out_mode = out_mode;
+    pp.cout = L.cout;
+    pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
+    pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
     if (const char* env = getenv("NNIC_TC_DBG")) pp.dbg = atoi(env);
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
@@ -590,25 +593,6 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     }
     return 0;
   }
-  CUtensorMap ma_hi, ma_lo;
-  if (int rc = make_act_map(h, &ma_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
-  if (int rc = make_act_map(h, &ma_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes)) return rc;
-  TcLayerParams prm;
-  memset(&prm, 0, sizeof prm);
-  prm.njobs = L.njobs;
-  memcpy(prm.jobs, L.jobs, sizeof L.jobs);
-  prm.P = P; prm.n_split = n_split; prm.Hp = Hp; prm.Wp = Wp; prm.Ho = Ho; prm.Wo = Wo; prm.out_stride = L.out_stride;
-  prm.rows_per_set = L.rows_per_set;
-  prm.inv_scale[0] = L.inv_scale[0]; prm.inv_scale[1] = L.inv_scale[1];
-  prm.bias = L.bias;
-  prm.res_hi = res ? res->hi : nullptr; prm.res_lo = res ? res->lo : nullptr;
-  prm.out_mode = out_mode;
-  prm.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
-  prm.out_hi = out.hi; prm.out_lo = out.lo;
-  prm.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
-  prm.out_u8 = out_u8; prm.out_prequant = out_prequant;
-  CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st, launch_tc_conv(L.row_bytes, L.cout, ma_hi, ma_lo, L.map_w_hi, L.map_w_lo, prm, h->num_sms, h->error_flag_dev, st));
-  return 0;
 }
 
 int pick_micro_batch(const nnic_t* h, int N, size_t pixels_per_image) {
@@ -771,7 +755,6 @@ int nnic_create(int device, nnic_t** out) {
     return fail(nullptr, NNIC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   }
   h->encode_tiled = (EncodeTiledFn)fn;
-  if (const char* env = getenv("NNIC_TC_PATCH")) h->tc_patch = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);

@@ -1,18 +1,28 @@
-// tcgen05 convolution, halo-patch variant, for the layers whose taps all lie in the 3x3 neighbourhood of the
-// output pixel: conv3, conv4 (encoder.py:12-13), dconv5, dconv6 and the four output phases of dconv7
-// (decoder.py:14-16).  64 input channels, 64 output channels.
+// tcgen05 convolution kernel for every GEMM-shaped layer of the codec: conv2, conv3, conv4, conv8
+// (encoder.py:11-17), dconv1, dconv5, dconv6 and the four output phases of dconv7 (decoder.py:11-16).
 //
-// tc_conv.cu streams one [128 pixel x 64 channel] activation tile per tap through shared memory; measured
-// with ncu, that kernel is bound by the shared-memory port (MMA operand reads ~125 B/clk plus TMA fills
-// ~107 B/clk against a 128 B/clk port).  Here the activation patch of a tile (18 rows x 10 columns of
-// pixels, 128 bytes each, SWIZZLE_128B) is loaded ONCE per work item and every tap reads it through a UMMA
-// descriptor whose start address is shifted by whole pixel rows and whose 8-row-group stride is the patch
-// pitch (10 pixels = 1280 bytes); tools/probe_tc.cu (probe A) shows the tensor core applies the 128-byte
-// swizzle on absolute shared-memory addresses, so such descriptors read exactly the shifted rows.  Only the
-// per-tap weight tiles (16 KB hi+lo) still stream, through an 8-deep ring.  For dconv7 one work item covers all
-// four output phases of a tile: they share the same patch (25 taps in total).
+// Work item = one tile of 16 x 8 output (or, for transposed convolutions, input) pixels of one plane.  All taps of
+// these layers lie in the 3x3 neighbourhood of the tile in the view the layer reads (the plain [C,W,1,H,P] view, or
+// the [2C,W/2,2,H/2,P] parity view for the stride-2 convolutions), so the activation patch of a tile (18 rows x 10
+// columns of pixels, 64 or 128 bytes each, hi and lo planes) is loaded ONCE per item by TMA (out-of-bounds zero fill =
+// TF SAME padding) and every tap reads it through a UMMA descriptor whose start address is shifted by whole pixel
+// rows and whose 8-row-group stride is the patch pitch (10 pixels); tools/probe_tc.cu (probe A) shows the tensor
+// core applies the swizzle on absolute shared-memory addresses, so such descriptors read exactly the shifted rows.
+// A first version streamed one [128 pixel x K] tile per tap instead and was bound by the shared-memory port (MMA
+// operand reads ~125 B/clk plus TMA fills ~107 B/clk against 128 B/clk, profiles/r1_ncu_tc_v1_streaming.txt).
+// Only the per-tap weight tiles [W_hi | W_lo] still stream, three taps per group.
+//   * stride-2 convolutions read one patch per input-row parity (conv2: column taps are paired in one 64-wide K slab)
+//     or per (row, column) parity (conv8: four patches, the column parity selects 64 of the view's 128 inner elements);
+//   * dconv7 / dconv1: one item covers all four output phases of a tile, they share the patch (25 taps in total).
 //
-// Arithmetic, accumulation chains, TMEM slot ring and epilogue are those of tc_conv.cu.
+// Arithmetic: operands are fp16 hi/lo pairs; per 16-wide k-step one MMA A_hi x [W_hi | W_lo] (N = 2*COUT) and one
+// A_lo x W_hi (N = COUT) accumulate into the two halves of a TMEM slot.  The tensor core truncates its fp32
+// accumulator on every MMA, so a slot only takes one chain of <= 3 taps (12 k-steps); the epilogue adds main and
+// correction halves and the chains with round-to-nearest fp32 adds, then bias, leaky ReLU, residual, and writes the
+// next layer's hi/lo planes (or, for conv8, clip + round(x*255) into the u8 latent).
+//
+// Warps: 0 weight TMA, 1-2 MMA issuers (alternate chains), 4*NSPLIT epilogue warps (TMEM lane group = warp % 4,
+// COUT/NSPLIT channels per thread, 256-bit global accesses), last warp patch TMA.  One persistent CTA per SM.
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -24,16 +34,17 @@ using namespace tc;
 
 constexpr int kNumMma = 2;                     // MMA issuer warps (2 = alternate chains)
 constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s), 4*NSPLIT epilogue warps, last warp patch TMA
-constexpr int COUT = 64;
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
 constexpr int GTAPS = 3;                                     // taps per accumulation chain = per weight group
 constexpr int WSLOTS = 2;                                    // weight groups in flight
-constexpr int SLOT_COLS = 2 * COUT, SLOTS = 4, TMEM_COLS = 512;
+constexpr int TMEM_COLS = 512;
 
 // RB = bytes of one pixel row of the patch (64 input channels -> 128, SWIZZLE_128B; 32 -> 64, SWIZZLE_64B)
-template <int RB, int NSPLIT>
+template <int RB, int NSPLIT, int COUT>
 struct PCfg {
+  static constexpr int SLOT_COLS = 2 * COUT;                             // one accumulation chain: [main | correction]
+  static constexpr int SLOTS = 512 / SLOT_COLS > 8 ? 8 : 512 / SLOT_COLS;
   static constexpr int kEpiWarps = 4 * NSPLIT;                          // NSPLIT warps per TMEM lane group, COUT/NSPLIT channels each
   static constexpr int kPatchWarp = kEpiWarp0 + kEpiWarps;
   static constexpr int kThreads = (kPatchWarp + 1) * 32;
@@ -65,13 +76,13 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int RB, int NSPLIT>
-__global__ void __launch_bounds__((PCfg<RB, NSPLIT>::kThreads), 1)
+template <int RB, int NSPLIT, int COUT>
+__global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
-  using C = PCfg<RB, NSPLIT>;
-  constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads;
+  using C = PCfg<RB, NSPLIT, COUT>;
+  constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
                 WG_BYTES = C::WG_BYTES, STG_WARP = C::STG_WARP, STG_OFF = C::STG_OFF, BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
   constexpr uint32_t A_SBO = C::A_SBO;
@@ -126,8 +137,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             mbar_arrive(&patch_full[pb]);
           } else {
             mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
-            tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], 0, X0 - 1, prm.patch_py[q], Y0 - 1, p);
-            tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], 0, X0 - 1, prm.patch_py[q], Y0 - 1, p);
+            tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
+            tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
           }
         }
         __syncwarp();
@@ -141,10 +152,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int p = it / tiles_per_plane;
       const int set = p < prm.n_split ? 0 : 1;
-      for (int j = 0; j < prm.njobs; ++j) {
-        const int nsteps = prm.jobs[j].nsteps;
-        for (int s0 = 0; s0 < nsteps; s0 += GTAPS) {          // one weight group = one accumulation chain
-          const int ntaps = nsteps - s0 < GTAPS ? nsteps - s0 : GTAPS;
+      const int nseg = prm.npatch;
+      for (int seg = 0; seg < nseg; ++seg) {
+      const int njobs_seg = nseg == 1 ? prm.njobs : 1;
+      for (int j = 0; j < njobs_seg; ++j) {
+        int sbeg = 0;
+        for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
+        const int send = nseg == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
+        for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one weight group = one accumulation chain
+          const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
           { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
             uint8_t* wb = w_base + ws * WG_BYTES;
@@ -162,6 +178,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           __syncwarp();
           if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
         }
+      }
       }
     }
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 0) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_w; }
@@ -182,7 +199,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
       const int njobs_seg = prm.npatch == 1 ? prm.njobs : 1;
       for (int j = 0; j < njobs_seg; ++j) {
-        const int sbeg = prm.npatch == 1 ? 0 : (seg == 0 ? 0 : prm.seg_steps[0]);
+        int sbeg = 0;
+        for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
         const int send = prm.npatch == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
         for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
           const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
@@ -309,14 +327,48 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], join_f32(rh[i], rl[i]));
           }
-          uint32_t h[HALF / 2], l[HALF / 2];
+          if (COUT == 32 && prm.clamp01) {
 #pragma unroll
-          for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
-          if (valid) {
+            for (int i = 0; i < HALF; ++i) acc[i] = fminf(fmaxf(acc[i], 0.0f), 1.0f);
+          }
+          if (COUT == 64 || prm.out_mode == TC_OUT_SPLIT) {
+            uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-            for (int q = 0; q < HALF / 16; ++q) {
-              st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
-              st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
+            for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < HALF / 16; ++q) {
+                st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
+                st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
+              }
+            }
+          } else if (prm.out_mode == TC_OUT_F32) {
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < HALF / 8; ++q) st_global_v8(prm.out_f32 + ooff + 8 * q, reinterpret_cast<const uint32_t*>(acc) + 8 * q);
+            }
+          } else {
+            // conv8: np.round(e*255).astype(uint8) (encoder.py:47) into the latent [N,Ho,Wo,96]; plane-major batch
+            // p = plane*N + n, channels plane*32 + channel
+            const int N = prm.P / 3;
+            const int plane = p / N, n = p - plane * N;
+            const size_t lo_ = (((size_t)n * prm.Ho + ooy) * prm.Wo + oox) * 96 + plane * 32 + ch0;
+            uint32_t q[HALF / 4];
+#pragma unroll
+            for (int i = 0; i < HALF; i += 4) {
+              uint32_t w = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w |= (uint32_t)(uint8_t)rintf(__fmul_rn(acc[i + e], 255.0f)) << (8 * e);
+              q[i / 4] = w;
+            }
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < HALF / 4; i += 4)
+                *reinterpret_cast<uint4*>(prm.out_u8 + lo_ + 4 * i) = make_uint4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+              if (prm.out_prequant) {
+#pragma unroll
+                for (int qq = 0; qq < HALF / 8; ++qq) st_global_v8(prm.out_prequant + lo_ + 8 * qq, reinterpret_cast<const uint32_t*>(acc) + 8 * qq);
+              }
             }
           }
         }
@@ -338,13 +390,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT>
+template <int RB, int NSPLIT, int COUT>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -352,7 +404,7 @@ static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap&
   const long long items = (long long)tiles_x * tiles_y * prm.P;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_conv_patch<RB, NSPLIT><<<grid, PCfg<RB, NSPLIT>::kThreads, PCfg<RB, NSPLIT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
+  k_tc_conv_patch<RB, NSPLIT, COUT><<<grid, PCfg<RB, NSPLIT, COUT>::kThreads, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
   return cudaGetLastError();
 }
 
@@ -361,9 +413,10 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
                                  cudaStream_t stream) {
   // layers whose epilogue is the limiter (residual add, or several output phases per work item) use 16 epilogue warps
   const bool heavy_epilogue = prm.res_hi != nullptr || prm.njobs > 1;
-  if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
-  if (row_bytes == 128) return launch_patch_impl<128, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
-  if (row_bytes == 64) return launch_patch_impl<64, 4>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 128 && prm.cout == 32) return launch_patch_impl<128, 2, 32>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 128) return launch_patch_impl<128, 2, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (row_bytes == 64) return launch_patch_impl<64, 4, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   return cudaErrorInvalidValue;
 }
 
