@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnnic.so")
+# NNIC_LIB: development override (e.g. the -DNNIC_TC_TIMERS build used by tools/); the product library sits next to this file
+LIB_PATH = os.environ.get("NNIC_LIB") or os.path.join(_HERE, "libnnic.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ARITH_TC_SPLIT, ARITH_SIMT_F32 = 0, 1

@@ -36,8 +36,8 @@ constexpr int kNumMma = 2;                     // MMA issuer warps (2 = alternat
 constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s), 4*NSPLIT epilogue warps, last warp patch TMA
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
-constexpr int GTAPS = 3;                                     // taps per accumulation chain = per weight group
-constexpr int WSLOTS = 2;                                    // weight groups in flight
+constexpr int GTAPS = 3;                                     // taps per accumulation chain
+constexpr int WSLOTS = 8;                                    // weight tiles (one tap each) in flight
 constexpr int TMEM_COLS = 512;
 
 // RB = bytes of one pixel row of the patch (64 input channels -> 128, SWIZZLE_128B; 32 -> 64, SWIZZLE_64B)
@@ -54,12 +54,8 @@ struct PCfg {
   static constexpr int SET_BYTES = 2 * PATCH_SLOT;                       // hi + lo
   static constexpr int W_TILE = COUT * RB;                               // one of hi / lo
   static constexpr int W_SLOT = 2 * W_TILE;                              // one tap: [W_hi | W_lo]
-  static constexpr int WG_BYTES = GTAPS * W_SLOT;
-  static constexpr int STG_WARP = 32 * (COUT / NSPLIT) * 2;              // per-epilogue-warp staging: 32 pixels x HALF fp16
-  static constexpr int STG_BYTES = kEpiWarps * STG_WARP;
-  static constexpr int STG_OFF = NSETS * SET_BYTES + WSLOTS * WG_BYTES;
-  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2 * COUT * 4 + 1024;
+  static constexpr int BAR_OFF = NSETS * SET_BYTES + WSLOTS * W_SLOT;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 2 * COUT * 4 + 1024;
   static constexpr uint32_t A_SBO = PW * RB;                             // 8-row group stride of a tap view: one patch row
   static constexpr uint64_t LAYOUT = RB == 128 ? 2ull : 4ull;            // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
   static constexpr uint32_t W_SBO = 8 * RB;
@@ -84,12 +80,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   using C = PCfg<RB, NSPLIT, COUT>;
   constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
-                WG_BYTES = C::WG_BYTES, STG_WARP = C::STG_WARP, STG_OFF = C::STG_OFF, BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
+                BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
   constexpr uint32_t A_SBO = C::A_SBO;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patch_base = smem;                                  // [NSETS][hi | lo]
-  uint8_t* w_base = smem + NSETS * SET_BYTES;                  // [WSLOTS][GTAPS][W_hi | W_lo]
+  uint8_t* w_base = smem + NSETS * SET_BYTES;                  // [WSLOTS][W_hi | W_lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* patch_full = bars;                 // [NSETS]
   uint64_t* patch_empty = bars + NSETS;        // [NSETS]
@@ -98,8 +94,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* slot_full = w_empty + WSLOTS;      // [SLOTS]
   uint64_t* slot_empty = slot_full + SLOTS;    // [SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
-  float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 256);
-  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 256, "barrier area too small");
+  float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 512);
+  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 512, "barrier area too small");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,20 +155,17 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int sbeg = 0;
         for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
         const int send = nseg == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
-        for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one weight group = one accumulation chain
-          const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
+        for (int s0 = sbeg; s0 < send; ++s0) {                 // one weight tile per tap, in the order the issuers consume them
           { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
-            uint8_t* wb = w_base + ws * WG_BYTES;
+            uint8_t* wb = w_base + ws * W_SLOT;
             if (prm.dbg & 4) {
               mbar_arrive(&w_full[ws]);
             } else {
-              mbar_expect_tx(&w_full[ws], ntaps * W_SLOT);
-              for (int k = 0; k < ntaps; ++k) {
-                const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s0 + k].w_row;
-                tma_load_2d(&map_w_hi, wb + k * W_SLOT, &w_full[ws], 0, wrow);
-                tma_load_2d(&map_w_lo, wb + k * W_SLOT + W_TILE, &w_full[ws], 0, wrow);
-              }
+              mbar_expect_tx(&w_full[ws], W_SLOT);
+              const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s0].w_row;
+              tma_load_2d(&map_w_hi, wb, &w_full[ws], 0, wrow);
+              tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
             }
           }
           __syncwarp();
@@ -205,28 +198,29 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
           const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
           if (kNumMma == 2 && ((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
-            if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
+            ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
             continue;
           }
           uint32_t a_off[GTAPS];
 #pragma unroll
           for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
-          { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); long long t1 = TICK(); tw_slot += t1 - t0;
-            mbar_wait(&w_full[ws], wphase, error_flag, 5); tw_w += TICK() - t1; }
+          { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); tw_slot += TICK() - t0; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
-          const uint64_t w0 = make_desc_sbo(w_u32 + ws * WG_BYTES, C::W_SBO, C::LAYOUT);   // tap k: + k*W_SLOT; W_hi followed by W_lo
           const long long ti0 = TICK();
-          if (elect_one()) {
-            if (!(prm.dbg & 1)) {
-              uint32_t accumulate = 0u;
+          if (elect_one()) {                     // one lane waits for each tap's weights, issues its MMAs and releases the tile
+            uint32_t accumulate = 0u;
+            int w = ws; uint32_t wp = wphase;
 #pragma unroll
-              for (int k = 0; k < GTAPS; ++k) {
-                if (k < ntaps) {
+            for (int k = 0; k < GTAPS; ++k) {
+              if (k < ntaps) {
+                { long long t1 = TICK(); mbar_wait(&w_full[w], wp, error_flag, 5); tw_w += TICK() - t1; }
+                tc_fence_after();
+                if (!(prm.dbg & 1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
-                  const uint64_t w_hl = w0 + (uint64_t)((k * W_SLOT) >> 4);
+                  const uint64_t w_hl = make_desc_sbo(w_u32 + w * W_SLOT, C::W_SBO, C::LAYOUT);   // W_hi followed by W_lo
                   const int ks_begin = (a_off[k] >> 31) ? KSTEPS / 2 : 0;
 #pragma unroll
                   for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -237,14 +231,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                   }
                 }
+                umma_commit(&w_empty[w]);
+                if (++w == WSLOTS) { w = 0; wp ^= 1; }
               }
             }
-            umma_commit(&w_empty[ws]);
             umma_commit(&slot_full[slot]);
           }
           __syncwarp();
+          ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
           t_issue += TICK() - ti0;
-          if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
         }
       }
