@@ -22,12 +22,15 @@ __device__ __forceinline__ void split_f32(float v, __half& hi, __half& lo) {
 }
 // Two values at once: {hi(v0), hi(v1)} and {lo(v0), lo(v1)} as packed fp16 pairs (v0 in the low half).  The
 // saturating pack instruction (F2FP.SATFINITE) replaces the explicit clamp of split_f32.
-__device__ __forceinline__ void split2_f32(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
-  const float s0 = v0 * ACT_SCALE, s1 = v1 * ACT_SCALE;
+// split2_scaled takes values that already carry the factor ACT_SCALE.
+__device__ __forceinline__ void split2_scaled(float s0, float s1, uint32_t& hi2, uint32_t& lo2) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(s1), "f"(s0));
   const float f0 = __half2float(__ushort_as_half((unsigned short)(hi2 & 0xffffu)));
   const float f1 = __half2float(__ushort_as_half((unsigned short)(hi2 >> 16)));
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(s1 - f1), "f"(s0 - f0));
+}
+__device__ __forceinline__ void split2_f32(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
+  split2_scaled(v0 * ACT_SCALE, v1 * ACT_SCALE, hi2, lo2);
 }
 __device__ __forceinline__ float join_f32(__half hi, __half lo) {
   return (__half2float(hi) + __half2float(lo)) * ACT_INV_SCALE;

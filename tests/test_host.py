@@ -103,3 +103,18 @@ def test_shard_ranges_partition(nn):
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sr(4, 2, 2)
+
+
+def test_div255_refinement():
+    """tc_conv1.cu computes x.astype(float32)/255 (encoder.py:39) as q = RN(x*RN(1/255)) plus one residual step;
+    the result must equal the IEEE quotient for every byte value (emulated here with exact double products)."""
+    x = np.arange(256, dtype=np.float32)
+    ref = (x / np.float32(255)).astype(np.float32)
+    y = np.float32(1) / np.float32(255)
+    assert float(y) == float.fromhex("0x1.010102p-8")
+    q = (x * y).astype(np.float32)
+    r = x.astype(np.float64) - q.astype(np.float64) * 255.0          # fma(-q, 255, x): exact, fits in fp32
+    assert np.array_equal(r, r.astype(np.float32).astype(np.float64))
+    q2 = (q.astype(np.float64) + r * np.float64(y)).astype(np.float32)
+    assert np.array_equal(q2, ref)
+    assert not np.array_equal(q, ref)      # the plain reciprocal multiply is not enough
