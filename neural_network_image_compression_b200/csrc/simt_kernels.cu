@@ -604,15 +604,17 @@ cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, u
   return cudaGetLastError();
 }
 
+// hist_global[i] += sum over images of hist[n][i]; blockIdx.y strides over the images, one 64-bit atomic per block and bin
 __global__ void __launch_bounds__(256) k_hist_reduce(const uint32_t* __restrict__ hist, int N,
                                                      unsigned long long* __restrict__ hist_global) {
   const int i = blockIdx.x * 256 + threadIdx.x;   // 0..767
   unsigned long long s = 0;
-  for (int n = 0; n < N; ++n) s += hist[(size_t)n * 768 + i];
-  hist_global[i] += s;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) s += hist[(size_t)n * 768 + i];
+  if (s) atomicAdd(&hist_global[i], s);
 }
 cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* hist_global, cudaStream_t stream) {
-  k_hist_reduce<<<3, 256, 0, stream>>>(hist, N, hist_global);
+  const int slices = N < 148 ? N : 148;
+  k_hist_reduce<<<dim3(3, slices < 1 ? 1 : slices), 256, 0, stream>>>(hist, N, hist_global);
   return cudaGetLastError();
 }
 
