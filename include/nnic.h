@@ -111,6 +111,13 @@ int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int l
 int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, int W, uint32_t* hist,
               float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream);
 
+/* Encode and rate in one pass: Encoder.__call__ followed by the histogram block above, with the symbol counts
+ * taken inside the kernel that quantises the latent (conv8's epilogue: shared-memory histogram of the tile,
+ * flushed with one global atomic per non-empty bin), so the latent is not read again.  Outputs as in nnic_encode
+ * and nnic_rate; results are identical to calling the two one after the other. */
+int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, uint32_t* hist,
+                     float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream);
+
 /* Entropy of already-reduced counts (e.g. hist_global after the cross-rank allreduce):
  *   counts uint64 [rows][256] -> entropy_bits float [rows].  Same formula as nnic_rate. */
 int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits,

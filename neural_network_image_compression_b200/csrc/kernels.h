@@ -104,6 +104,7 @@ struct TcPatchParams {
   int clamp01;                // clip the activation to [0,1] (conv8: encoder.py:32)
   uint8_t* out_u8;            // TC_OUT_QUANT: latent [N,Ho,Wo,96], N = P/3
   float* out_prequant;        // TC_OUT_QUANT, optional: f32 [N,Ho,Wo,96]
+  uint32_t* hist;             // TC_OUT_QUANT, optional: [N][3][256] symbol counts, added to (tf1_13/src/training.py:62-68)
   long long* dbg_buf;         // development: per-CTA role timers [grid][4][8] (NNIC_TC_PROF)
   int dbg;                    // development switches (NNIC_TC_DBG): 1 skip MMAs, 2 skip stores, 4 skip W loads, 8 skip TMEM loads
   __half* out_hi;

@@ -70,6 +70,7 @@ struct nnic_handle {
   std::string err;
   uint64_t launches = 0;
   int micro_batch = 0;
+  uint32_t* fused_hist = nullptr;   // set around conv8's launch by encode_batch: device [nb][3][256] counts to add to
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   EncodeTiledFn encode_tiled = nullptr;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
@@ -568,6 +569,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.cout = L.cout;
     pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
     pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
+    pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
     if (const char* env = getenv("NNIC_TC_DBG")) pp.dbg = atoi(env);
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
@@ -606,8 +608,9 @@ int pick_micro_batch(const nnic_t* h, int N, size_t pixels_per_image) {
 
 // ---- encoder for one micro-batch -----------------------------------------------------------------
 // in: rgb u8 [nb,H,W,3] (device) or f32 planes [3nb,H,W,1] (device).  Outputs are device pointers.
+// hist: optional device [nb][3][256] u32, already zeroed; the symbol counts of this micro-batch are added to it
 int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int H, int W, uint8_t* latent,
-                 float* prequant, float* out_planes, cudaStream_t st) {
+                 float* prequant, float* out_planes, uint32_t* hist, cudaStream_t st) {
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
   const int P = 3 * nb;
   int H1, W1, H2, W2, H3, W3, t;
@@ -644,7 +647,10 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
     if (out_planes) {
       if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, out_planes, st)) return rc;
     } else {
-      if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_QUANT, latent, prequant, nullptr, st)) return rc;
+      h->fused_hist = hist;                      // conv8's epilogue counts the symbols it writes
+      const int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_QUANT, latent, prequant, nullptr, st);
+      h->fused_hist = nullptr;
+      if (rc) return rc;
     }
   } else {
     if (out_planes) {
@@ -653,6 +659,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
       a5 = take_act(h, false, P, H3, W3, 32);
       if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, nullptr, st)) return rc;
       CKL(h, K_QUANTISE, st, launch_quantise(a5.f32, nb, H3, W3, latent, prequant, st));
+      if (hist) CKL(h, K_HIST, st, launch_hist(latent, nb, (size_t)H3 * W3, hist, st));
     }
   }
   record_dbg(h, 0, a1, P); record_dbg(h, 1, a2, P); record_dbg(h, 2, a3, P); record_dbg(h, 3, a4, P);
@@ -824,8 +831,9 @@ int nnic_set_weights(nnic_t* h, int set, int layer, const float* kernel, const f
   return NNIC_OK;
 }
 
-int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, float* prequant, int mem_kind,
-                void* stream) {
+// d_hist: optional DEVICE buffer [N][3][256] u32 (zeroed by the caller on `stream`) that receives the symbol counts
+static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, float* prequant, uint32_t* d_hist,
+                       int mem_kind, void* stream) {
   if (!h) return NNIC_ERR_INVALID_ARG;
   if (!rgb || !latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: non-positive shape %dx%dx%d", N, H, W);
@@ -867,18 +875,23 @@ int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* lat
       CK(h, cudaMemcpyAsync(d_rgb[s2], src, nb * img_px * 3, cudaMemcpyHostToDevice, h->h2d_stream));
       CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
       CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
-      if (int rc = encode_batch(h, d_rgb[s2], nullptr, nb, H, W, d_lat[s2], d_pre[s2], nullptr, st)) return rc;
+      if (int rc = encode_batch(h, d_rgb[s2], nullptr, nb, H, W, d_lat[s2], d_pre[s2], nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
       CK(h, cudaEventRecord(h->ev_comp[s2], st));
       CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
       CK(h, cudaMemcpyAsync(dst, d_lat[s2], nb * lat_px * 96, cudaMemcpyDeviceToHost, h->d2h_stream));
       if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
       CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
     } else {
-      if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, st)) return rc;
+      if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
     }
   }
   if (host) { CK(h, cudaStreamSynchronize(h->d2h_stream)); CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
   return NNIC_OK;
+}
+
+int nnic_encode(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, float* prequant, int mem_kind,
+                void* stream) {
+  return encode_impl(h, rgb, N, H, W, latent, prequant, nullptr, mem_kind, stream);
 }
 
 int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t* rgb, float* prequant, int mem_kind,
@@ -958,7 +971,7 @@ int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W,
     CK(h, cudaMemcpyAsync(t_in, planes, in_elems * 4, cudaMemcpyHostToDevice, st));
     d_in = t_in;
   }
-  if (int rc = encode_batch(h, nullptr, d_in, N, H, W, nullptr, nullptr, d_out, st)) return rc;
+  if (int rc = encode_batch(h, nullptr, d_in, N, H, W, nullptr, nullptr, d_out, nullptr, st)) return rc;
   if (host) {
     CK(h, cudaMemcpyAsync(out, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
@@ -996,6 +1009,52 @@ int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int l
   return NNIC_OK;
 }
 
+// Rate outputs: device scratch (host callers) or the caller's device buffers.
+struct RateBufs {
+  uint32_t* d_hist; float* d_ent; float* d_bpp; unsigned long long* d_glob; uint8_t* d_lat;
+};
+static int rate_setup(nnic_t* h, int N, size_t lat_bytes_host, uint32_t* hist, float* entropy_bits, float* bpp,
+                      uint64_t* hist_global, bool host, cudaStream_t st, RateBufs& rb) {
+  const size_t hist_bytes = (size_t)N * 768 * 4;
+  size_t need = pad1k(hist_bytes) + pad1k((size_t)N * 3 * 4) + pad1k((size_t)N * 4) + pad1k(768 * 8) + pad1k(lat_bytes_host) + 8192;
+  if (int rc = ensure_buf(h, h->rate_scratch, need)) return rc;
+  uint8_t* base = (uint8_t*)h->rate_scratch.ptr;
+  size_t off = 0;
+  auto take = [&](size_t b) { void* p = base + off; off += pad1k(b); return p; };
+  rb.d_hist = (uint32_t*)take(hist_bytes);
+  rb.d_ent = (float*)take((size_t)N * 3 * 4);
+  rb.d_bpp = (float*)take((size_t)N * 4);
+  rb.d_glob = (unsigned long long*)take(768 * 8);
+  rb.d_lat = lat_bytes_host ? (uint8_t*)take(lat_bytes_host) : nullptr;
+  if (!host) {
+    if (hist) rb.d_hist = hist;
+    if (entropy_bits) rb.d_ent = entropy_bits;
+    if (bpp) rb.d_bpp = bpp;
+    if (hist_global) rb.d_glob = (unsigned long long*)hist_global;
+  }
+  CK(h, cudaMemsetAsync(rb.d_hist, 0, hist_bytes, st));
+  return 0;
+}
+// entropy / bpp / global counts from rb.d_hist, and the copies back for host callers
+static int rate_finish(nnic_t* h, int N, int lh, int lw, int H, int W, uint32_t* hist, float* entropy_bits, float* bpp,
+                       uint64_t* hist_global, bool host, cudaStream_t st, const RateBufs& rb) {
+  const size_t hist_bytes = (size_t)N * 768 * 4;
+  if (entropy_bits || bpp)
+    CKL(h, K_ENTROPY, st, launch_entropy_u32(rb.d_hist, N, (float)((size_t)lh * lw * 32), (float)((size_t)H * W), rb.d_ent, rb.d_bpp, st));
+  if (hist_global) {
+    if (host) CK(h, cudaMemcpyAsync(rb.d_glob, hist_global, 768 * 8, cudaMemcpyHostToDevice, st));
+    CKL(h, K_HIST_REDUCE, st, launch_hist_reduce(rb.d_hist, N, rb.d_glob, st));
+  }
+  if (host) {
+    if (hist) CK(h, cudaMemcpyAsync(hist, rb.d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
+    if (entropy_bits) CK(h, cudaMemcpyAsync(entropy_bits, rb.d_ent, (size_t)N * 3 * 4, cudaMemcpyDeviceToHost, st));
+    if (bpp) CK(h, cudaMemcpyAsync(bpp, rb.d_bpp, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (hist_global) CK(h, cudaMemcpyAsync(hist_global, rb.d_glob, 768 * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+  }
+  return NNIC_OK;
+}
+
 int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, int W, uint32_t* hist, float* entropy_bits,
               float* bpp, uint64_t* hist_global, int mem_kind, void* stream) {
   if (!h) return NNIC_ERR_INVALID_ARG;
@@ -1006,43 +1065,29 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
   cudaStream_t st = (cudaStream_t)stream;
   const bool host = mem_kind == NNIC_MEM_HOST;
   const size_t lat_bytes = (size_t)N * lh * lw * 96;
-  const size_t hist_bytes = (size_t)N * 768 * 4;
-  size_t need = pad1k(hist_bytes) + pad1k((size_t)N * 3 * 4) + pad1k((size_t)N * 4) + pad1k(768 * 8) + (host ? pad1k(lat_bytes) : 0) + 8192;
-  if (int rc = ensure_buf(h, h->rate_scratch, need)) return rc;
-  uint8_t* base = (uint8_t*)h->rate_scratch.ptr;
-  size_t off = 0;
-  auto take = [&](size_t b) { void* p = base + off; off += pad1k(b); return p; };
-  uint32_t* d_hist = (uint32_t*)take(hist_bytes);
-  float* d_ent = (float*)take((size_t)N * 3 * 4);
-  float* d_bpp = (float*)take((size_t)N * 4);
-  unsigned long long* d_glob = (unsigned long long*)take(768 * 8);
+  RateBufs rb;
+  if (int rc = rate_setup(h, N, host ? lat_bytes : 0, hist, entropy_bits, bpp, hist_global, host, st, rb)) return rc;
   const uint8_t* d_lat = latent;
   if (host) {
-    uint8_t* t = (uint8_t*)take(lat_bytes);
-    CK(h, cudaMemcpyAsync(t, latent, lat_bytes, cudaMemcpyHostToDevice, st));
-    d_lat = t;
-  } else {
-    if (hist) d_hist = hist;
-    if (entropy_bits) d_ent = entropy_bits;
-    if (bpp) d_bpp = bpp;
-    if (hist_global) d_glob = (unsigned long long*)hist_global;
+    CK(h, cudaMemcpyAsync(rb.d_lat, latent, lat_bytes, cudaMemcpyHostToDevice, st));
+    d_lat = rb.d_lat;
   }
-  CK(h, cudaMemsetAsync(d_hist, 0, hist_bytes, st));
-  CKL(h, K_HIST, st, launch_hist(d_lat, N, (size_t)lh * lw, d_hist, st));
-  if (entropy_bits || bpp)
-    CKL(h, K_ENTROPY, st, launch_entropy_u32(d_hist, N, (float)((size_t)lh * lw * 32), (float)((size_t)H * W), d_ent, d_bpp, st));
-  if (hist_global) {
-    if (host) CK(h, cudaMemcpyAsync(d_glob, hist_global, 768 * 8, cudaMemcpyHostToDevice, st));
-    CKL(h, K_HIST_REDUCE, st, launch_hist_reduce(d_hist, N, d_glob, st));
-  }
-  if (host) {
-    if (hist) CK(h, cudaMemcpyAsync(hist, d_hist, hist_bytes, cudaMemcpyDeviceToHost, st));
-    if (entropy_bits) CK(h, cudaMemcpyAsync(entropy_bits, d_ent, (size_t)N * 3 * 4, cudaMemcpyDeviceToHost, st));
-    if (bpp) CK(h, cudaMemcpyAsync(bpp, d_bpp, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
-    if (hist_global) CK(h, cudaMemcpyAsync(hist_global, d_glob, 768 * 8, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
-  }
-  return NNIC_OK;
+  CKL(h, K_HIST, st, launch_hist(d_lat, N, (size_t)lh * lw, rb.d_hist, st));
+  return rate_finish(h, N, lh, lw, H, W, hist, entropy_bits, bpp, hist_global, host, st, rb);
+}
+
+int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, uint32_t* hist,
+                     float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode_rate: non-positive shape %dx%dx%d", N, H, W);
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  RateBufs rb;
+  if (int rc = rate_setup(h, N, 0, hist, entropy_bits, bpp, hist_global, host, st, rb)) return rc;
+  if (int rc = encode_impl(h, rgb, N, H, W, latent, nullptr, rb.d_hist, mem_kind, stream)) return rc;
+  return rate_finish(h, N, (H + 7) / 8, (W + 7) / 8, H, W, hist, entropy_bits, bpp, hist_global, host, st, rb);
 }
 
 int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits, int mem_kind, void* stream) {

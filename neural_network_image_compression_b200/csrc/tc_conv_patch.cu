@@ -55,7 +55,8 @@ struct PCfg {
   static constexpr int W_TILE = COUT * RB;                               // one of hi / lo
   static constexpr int W_SLOT = 2 * W_TILE;                              // one tap: [W_hi | W_lo]
   static constexpr int BAR_OFF = NSETS * SET_BYTES + WSLOTS * W_SLOT;
-  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 2 * COUT * 4 + 1024;
+  static constexpr int HIST_OFF = BAR_OFF + 512 + 2 * COUT * 4;          // conv8: 256-bin histogram of the tile being quantised
+  static constexpr int SMEM_BYTES = HIST_OFF + 1024 + 1024;
   static constexpr uint32_t A_SBO = PW * RB;                             // 8-row group stride of a tap view: one patch row
   static constexpr uint64_t LAYOUT = RB == 128 ? 2ull : 4ull;            // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
   static constexpr uint32_t W_SBO = 8 * RB;
@@ -95,6 +96,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* slot_empty = slot_full + SLOTS;    // [SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 512);
+  uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem + C::HIST_OFF);
   static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 512, "barrier area too small");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -109,6 +111,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
   }
   for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) bias_s[i] = prm.bias[i];
+  for (int i = threadIdx.x; i < 256; i += kThreads) hist_s[i] = 0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -355,6 +358,30 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
               for (int e = 0; e < 4; ++e) w |= (uint32_t)(uint8_t)rintf(__fmul_rn(acc[i + e], 255.0f)) << (8 * e);
               q[i / 4] = w;
+            }
+            if (prm.hist) {
+              // Histogram of the tile (tf1_13/src/training.py:62-68), counted where the symbols are produced.  All 128
+              // pixels of an item belong to one (image, plane): shared-memory atomics for the non-zero symbols, zeros
+              // counted per warp, then the kEpiWarps*32 = 256 epilogue threads flush one bin each.
+              static_assert(COUT != 32 || kEpiWarps * 32 == 256, "one flushing thread per bin");
+              uint32_t zeros = 0;
+              if (valid) {
+#pragma unroll
+                for (int i = 0; i < HALF / 4; ++i) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const uint32_t sym = (q[i] >> (8 * e)) & 0xffu;
+                    if (sym) atomicAdd(&hist_s[sym], 1u); else ++zeros;
+                  }
+                }
+              }
+              zeros = __reduce_add_sync(0xffffffffu, zeros);
+              if (lane == 0 && zeros) atomicAdd(&hist_s[0], zeros);
+              asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+              const int bin = (warp - kEpiWarp0) * 32 + lane;
+              const uint32_t cnt = hist_s[bin];
+              if (cnt) { atomicAdd(prm.hist + ((size_t)n * 3 + plane) * 256 + bin, cnt); hist_s[bin] = 0; }
+              asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
             }
             if (valid) {
 #pragma unroll

@@ -193,6 +193,39 @@ def test_rate_edge_cases(nn, codec_factory):
     assert abs(bpp_g - float(O.entropy_from_hist(want).sum() * 0.5)) < 1e-4
 
 
+@pytest.mark.parametrize("arith,shape", [("tc_split", (5, 64, 96)), ("tc_split", (3, 200, 136)), ("tc_split", (2, 8, 8)),
+                                         ("simt_f32", (2, 52, 44))])
+def test_fused_encode_rate_equals_encode_then_rate(nn, codec_factory, arith, shape):
+    """nnic_encode_rate counts the symbols inside the quantising kernel: latent, histograms, entropy and bpp must be
+    bit-identical to encode followed by the standalone rate pass, for host and device buffers, with tiles that hang
+    over the latent edge (200x136 -> 25x17 latent) and with micro-batches."""
+    import torch
+    enc, _ = codec_factory("spread", arith)
+    n, hh, ww = shape
+    x = synthetic_images(n, hh, ww, seed=21)
+    lat = enc(x)
+    want = nn.rate(enc.handle, lat, hh, ww)
+    for mb in (0, 1, 2):
+        enc.handle.set_micro_batch(mb)
+        lat2, got = enc.encode_rate(x)
+        assert np.array_equal(lat2, lat)
+        assert np.array_equal(got.hist, want.hist)
+        assert np.array_equal(got.hist_global, want.hist_global)
+        assert np.array_equal(got.entropy_bits, want.entropy_bits)
+        assert np.array_equal(got.bpp, want.bpp)
+        assert int(got.hist.sum()) == lat.size
+    enc.handle.set_micro_batch(0)
+    acc = torch.zeros((3, 256), dtype=torch.int64, device="cuda")
+    lat3, got3 = enc.encode_rate(torch.from_numpy(x).cuda(), hist_global=acc)
+    lat3b, _ = enc.encode_rate(torch.from_numpy(x).cuda(), hist_global=acc)     # accumulates
+    torch.cuda.synchronize()
+    assert np.array_equal(lat3.cpu().numpy(), lat)
+    assert np.array_equal(got3.hist.cpu().numpy().astype(np.uint32), want.hist)
+    assert np.array_equal(acc.cpu().numpy().astype(np.uint64), 2 * want.hist_global)
+    hist_o = O.histogram(lat)
+    assert np.array_equal(want.hist.astype(np.int64), hist_o)
+
+
 def test_argument_errors(nn, codec_factory):
     enc, dec = codec_factory("default", "tc_split")
     with pytest.raises(ValueError):
