@@ -3,12 +3,14 @@
 Public surface (mirrors /root/reference/tf2_0/src): Encoder, Decoder, ProClass, plus rate().
 All arithmetic runs in libnnic.so (hand-written sm_100a CUDA); there is no CPU fallback.
 """
-from . import dist, weights
+from . import container, dist, weights
 from ._lib import Handle, NnicError, colour_constants, load_library
 from .decoder import Decoder
 from .encoder import Encoder
+from .container import get_bpp, pack_latent, read_dataset, save_img, unpack_latent
 from .rate import Rate, entropy_from_counts, rate
 from .utils import ProClass
 
 __all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "Rate", "entropy_from_counts",
-           "weights", "dist", "colour_constants", "load_library"]
+           "weights", "dist", "container", "colour_constants", "load_library", "pack_latent", "unpack_latent", "read_dataset",
+           "save_img", "get_bpp"]

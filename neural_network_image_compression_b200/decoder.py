@@ -39,3 +39,9 @@ class Decoder(ProClass):
         pre = np.empty(out.shape, np.float32) if return_prequant else None
         self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_decode")
         return (out, pre) if return_prequant else out
+
+    def uncompress(self, dataset_path, checkpoint_path=None):
+        """decoder.py:50-52: every packed latent PNG of `dataset_path` (a `..._compressed` directory) ->
+        reconstruction PNG in the directory named with 'compressed' replaced by 'uncompressed'."""
+        return self._use_model(dataset_path, checkpoint_path, dataset_path.replace("compressed", "uncompressed"),
+                               in_cshape=96)

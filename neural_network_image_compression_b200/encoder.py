@@ -42,6 +42,11 @@ class Encoder(ProClass):
         self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_HOST, None), "nnic_encode")
         return (out, pre) if return_prequant else out
 
+    def compress(self, dataset_path, checkpoint_path=None):
+        """encoder.py:49-51: every colour image of `dataset_path` -> `<dataset_path>_compressed/<name>.png`, the
+        latent packed as a 4h x 8w RGB picture (container.pack_latent)."""
+        return self._use_model(dataset_path, checkpoint_path, dataset_path + "_compressed", in_cshape=3)
+
     def encode_rate(self, x, out=None, hist_global=None):
         """Encoder.__call__ plus the histogram/entropy rate of tf1_13/src/training.py:62-71 in one pass: the
         symbols are counted by the kernel that quantises them (nnic_encode_rate), the latent is not read again.

@@ -13,6 +13,7 @@ import numpy as np
 
 from . import weights as W
 from ._lib import MEM_DEVICE, MEM_HOST, Handle, NnicError, _ptr
+from .container import DatasetDriver, read_dataset, save_img  # noqa: F401  (utils.py:30-62,85-120)
 
 _MODELS = list(W.MODEL_SUFFIXES)
 
@@ -31,7 +32,7 @@ def _stream_of(x):
     return torch.cuda.current_stream(x.device).cuda_stream
 
 
-class ProClass:
+class ProClass(DatasetDriver):
     """Pair of networks of one kind ('encoder' or 'decoder') on one GPU."""
 
     kind = None  # set by subclasses

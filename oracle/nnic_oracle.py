@@ -247,6 +247,31 @@ def rate(latent_u8: np.ndarray, H: int, W: int, mode: str = "f32"):
     return hist, ent, bpp, hist.sum(axis=0)
 
 
+def pack_latent(latent_u8: np.ndarray):
+    """utils.py:42-44 (`_feed_batch`, c == 96): picture[n, y, x, i] = byte number y*8w + x of the C-order stream of
+    latent[n, :, :, 32i:32i+32].  Written as index arithmetic, independently of the product's reshape."""
+    n, h, w, _ = latent_u8.shape
+    flat = np.arange(4 * h * 8 * w).reshape(4 * h, 8 * w)
+    pix, ch = flat // 32, flat % 32
+    rows, cols = pix // w, pix % w
+    out = np.empty((n, 4 * h, 8 * w, 3), np.uint8)
+    for i in range(3):
+        out[..., i] = latent_u8[:, rows, cols, 32 * i + ch]
+    return out
+
+
+def unpack_latent(picture_u8: np.ndarray):
+    """utils.py:36-38 (`_feed_batch`, in_cshape == 96): the inverse mapping of pack_latent."""
+    n, hh, ww, _ = picture_u8.shape
+    h, w = hh // 4, ww // 8
+    out = np.empty((n, h, w, 96), np.uint8)
+    for i in range(3):
+        stream = picture_u8[..., i].reshape(n, -1)
+        for ch in range(32):
+            out[..., 32 * i + ch] = stream[:, ch::32].reshape(n, h, w)
+    return out
+
+
 def psnr(a_u8: np.ndarray, b_u8: np.ndarray):
     mse = np.mean((a_u8.astype(np.float64) - b_u8.astype(np.float64)) ** 2)
     return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)

@@ -290,3 +290,35 @@ def test_config5_patch_shard(nn, codec_factory):
     """256x256 patches (config 5 shape), a 256-patch shard: encode + global histogram."""
     sym = _cross_check(nn, codec_factory, synthetic_images(256, 256, 256, seed=5), check_decode=False)
     assert sym.shape == (256, 32, 32, 96)
+
+
+def test_compress_uncompress_directories(nn, codec_factory, tmp_path):
+    """Encoder.compress / Decoder.uncompress (encoder.py:49-51, decoder.py:50-52, utils.py:30-62): a directory of
+    images -> `<dir>_compressed/*.png` (packed latents) -> `<dir>_uncompressed/*.png`, equal to the in-memory path
+    and to the oracle's packing; weights go through save()/load() as `path+'Y'`, `path+'CbCr'`."""
+    from PIL import Image
+    enc, dec = codec_factory("spread", "tc_split")
+    imgs = synthetic_images(6, 64, 96, seed=31)           # 6 images: one full batch of 4 and a rest of 2
+    src = tmp_path / "kodak"
+    src.mkdir()
+    for i, im in enumerate(imgs):
+        nn.save_img(im, str(src), f"im{i:02d}")
+    enc.save(str(tmp_path / "encoder")); dec.save(str(tmp_path / "decoder"))
+    enc2, dec2 = nn.Encoder(0), nn.Decoder(0)
+    cdir = enc2.compress(str(src), str(tmp_path / "encoder"))
+    assert cdir == str(src) + "_compressed"
+    udir = dec2.uncompress(cdir, str(tmp_path / "decoder"))
+    assert udir == str(src) + "_uncompressed"
+    lat = enc(imgs)
+    rec = dec(lat)
+    packed = O.pack_latent(lat)
+    for i in range(6):
+        c = np.array(Image.open(f"{cdir}/im{i:02d}.png"))
+        u = np.array(Image.open(f"{udir}/im{i:02d}.png"))
+        assert c.shape == (4 * 8, 8 * 12, 3) and np.array_equal(c, packed[i])
+        assert u.shape == (64, 96, 3) and np.array_equal(u, rec[i])
+    # a directory with two image sizes is processed one image at a time
+    nn.save_img(synthetic_images(1, 32, 48, seed=32)[0], str(src), "small")
+    enc2.compress(str(src))
+    small = np.array(Image.open(f"{cdir}/small.png"))
+    assert np.array_equal(nn.unpack_latent(small[None]), enc(synthetic_images(1, 32, 48, seed=32)))

@@ -118,3 +118,55 @@ def test_div255_refinement():
     q2 = (q.astype(np.float64) + r * np.float64(y)).astype(np.float32)
     assert np.array_equal(q2, ref)
     assert not np.array_equal(q, ref)      # the plain reciprocal multiply is not enough
+
+
+# ---- file side of the codec: utils.py:30-62,85-120, training.py:12-21 -------------------------
+def test_pack_unpack_latent_against_oracle(nn):
+    from oracle import nnic_oracle as O
+    rng = np.random.default_rng(5)
+    for n, h, w in ((1, 1, 1), (2, 3, 5), (3, 8, 12)):
+        lat = rng.integers(0, 256, size=(n, h, w, 96), dtype=np.uint8)
+        pic = nn.pack_latent(lat)
+        assert pic.shape == (n, 4 * h, 8 * w, 3) and pic.dtype == np.uint8
+        assert np.array_equal(pic, O.pack_latent(lat))
+        assert np.array_equal(nn.unpack_latent(pic), lat)
+        assert np.array_equal(O.unpack_latent(pic), lat)
+    with pytest.raises(ValueError):
+        nn.pack_latent(np.zeros((1, 2, 2, 32), np.uint8))
+    with pytest.raises(ValueError):
+        nn.unpack_latent(np.zeros((1, 6, 8, 3), np.uint8))
+
+
+def test_read_dataset_and_save_img(nn, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(6)
+    d = tmp_path / "set"
+    d.mkdir()
+    imgs = {name: rng.integers(0, 256, size=(16, 24, 3), dtype=np.uint8) for name in ("b", "a", "c.x")}
+    for name, im in imgs.items():
+        nn.save_img(im, str(d), name)
+    Image.fromarray(rng.integers(0, 256, size=(16, 24), dtype=np.uint8)).save(d / "grey.png")   # skipped: not colour
+    (d / "notes.txt").write_text("not an image")
+    x, names = nn.read_dataset(str(d))
+    assert names == ["a", "b", "c.x"]                      # sorted file names, extension stripped
+    assert x.shape == (3, 16, 24, 3) and x.dtype == np.uint8
+    for i, name in enumerate(names):
+        assert np.array_equal(x[i], imgs[name])
+    nn.save_img(rng.integers(0, 256, size=(8, 8, 3), dtype=np.uint8), str(d), "d")              # another size: ragged set
+    x, names = nn.read_dataset(str(d))
+    assert isinstance(x, list) and [a.shape for a in x] == [(1, 16, 24, 3)] * 3 + [(1, 8, 8, 3)]
+    with pytest.raises(AssertionError):
+        nn.save_img(np.full((4, 4, 3), 0.5), str(d), "frac")
+
+
+def test_get_bpp_follows_the_reference_definition(nn):
+    """training.py:14-21: 8 * PNG bytes of the [4h, 8w] byte picture of each plane / pixels of that picture."""
+    rng = np.random.default_rng(7)
+    flat = np.zeros((2, 8, 12, 32), np.float32)
+    noise = rng.integers(0, 256, size=(2, 8, 12, 32)).astype(np.float32)
+    b0, b1 = nn.get_bpp(flat), nn.get_bpp(noise)
+    assert b0.shape == (2, 1) and b0.dtype == np.float32
+    assert (b1 > 7.0).all() and (b0 < 1.0).all()           # incompressible noise costs ~8 bits per byte (+ header)
+    pic = np.round(noise[0]).astype(np.uint8).reshape(32, 96)
+    assert b1[0, 0] == np.float32(8.0 * nn.container.png_size(pic) / (32 * 96))
+    assert np.allclose(nn.get_bpp(noise, tot_pixels_compressed=64 * 96), b1 * (32 * 96) / (64 * 96))
