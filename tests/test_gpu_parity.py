@@ -322,3 +322,41 @@ def test_compress_uncompress_directories(nn, codec_factory, tmp_path):
     enc2.compress(str(src))
     small = np.array(Image.open(f"{cdir}/small.png"))
     assert np.array_equal(nn.unpack_latent(small[None]), enc(synthetic_images(1, 32, 48, seed=32)))
+
+
+@pytest.mark.parametrize("shape", [(3, 72, 40), (1, 8, 8), (2, 136, 264)])
+def test_outputs_stay_inside_their_buffers(nn, codec_factory, shape):
+    """Every output is placed in the middle of a larger sentinel-filled device buffer: the kernels (partial tiles at
+    the right / bottom edge, 256-bit stores, the histogram flush) must not write one byte outside it."""
+    import torch
+    enc, dec = codec_factory("spread", "tc_split")
+    n, hh, ww = shape
+    lh, lw = hh // 8, ww // 8
+    x = torch.from_numpy(synthetic_images(n, hh, ww, seed=41)).cuda()
+    guard = 4096
+
+    def framed(numel, dtype, fill):
+        big = torch.full((numel + 2 * guard,), fill, dtype=dtype, device="cuda")
+        return big, big[guard:guard + numel]
+
+    big_lat, lat = framed(n * lh * lw * 96, torch.uint8, 0xA5)
+    big_pre, pre = framed(n * lh * lw * 96, torch.float32, -7.0)
+    big_rgb, rgb = framed(n * hh * ww * 3, torch.uint8, 0x5A)
+    big_hg, hg = framed(3 * 256, torch.int64, -1)
+    lat = lat.view(n, lh, lw, 96); rgb = rgb.view(n, hh, ww, 3)
+    hg.zero_()
+    hg = hg.view(3, 256)
+    # nnic_encode with the optional pre-quantisation output, then the fused encode + rate, then decode
+    h = enc.handle
+    h.check(h.lib.nnic_encode(h.h, x.data_ptr(), n, hh, ww, lat.data_ptr(), pre.data_ptr(), 1, None), "nnic_encode")
+    lat_a = lat.clone()
+    lat2, r = enc.encode_rate(x, out=lat, hist_global=hg)
+    dec(lat, out=rgb)
+    torch.cuda.synchronize()
+    for big, fill in ((big_lat, 0xA5), (big_pre, -7.0), (big_rgb, 0x5A), (big_hg, -1)):
+        assert bool((big[:guard] == fill).all()) and bool((big[-guard:] == fill).all())
+    assert torch.equal(lat_a, lat2) and int(hg.sum()) == lat.numel()
+    want_lat = enc(x.cpu().numpy())
+    assert np.array_equal(lat.cpu().numpy(), want_lat)
+    assert np.array_equal(rgb.cpu().numpy(), dec(want_lat))
+    assert np.array_equal(np.round(pre.view(n, lh, lw, 96).cpu().numpy() * np.float32(255)).astype(np.uint8), want_lat)
