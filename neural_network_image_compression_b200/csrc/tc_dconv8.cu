@@ -10,9 +10,10 @@
 // One work item = 14 x 6 input pixels of one image (+ one pixel of halo = one 16 x 8 = 128-pixel A tile)
 // -> 28 x 12 output pixels, all three colour planes (plane 0 with the 'Y' weights, planes 1/2 with 'CbCr').
 // Per plane: one TMA load of the tile (hi, lo), 4 k-steps x 2 MMAs (A_hi x [W_hi|W_lo] with N = 64, A_lo x W_hi
-// with N = 32), accumulator [main 32 | corr 32] in one of eight TMEM slots.  The four epilogue warps read R,
-// exchange it through shared memory, gather the outputs in a fixed order, and after the third plane apply the
-// colour transform and store packed RGB bytes.
+// with N = 32), accumulator [main 32 | corr 32] in one of eight TMEM slots.  Four epilogue warps read R, exchange
+// it through shared memory, gather the outputs in a fixed order, and after the third plane apply the colour
+// transform and store packed RGB bytes.  The epilogue is the long pole (a few hundred dependent instructions per
+// thread and item on one warp per scheduler), so two such teams of four warps work on alternate items.
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -22,24 +23,27 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;                 // warp 0 TMA, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kTeams = 2;                     // epilogue teams (4 warps = 128 TMEM lanes each) on alternate items
+constexpr int kThreads = (2 + 4 * kTeams) * 32;   // warp 0 TMA, warp 1 MMA issuer, then the epilogue warps
 constexpr int NT = 32;                        // taps padded to the MMA N granularity
 constexpr int IH = kTileRows - 2, IW = kTileCols - 2;   // interior input pixels per item: 14 x 6
 constexpr int OH = 2 * IH, OW = 2 * IW;       // output pixels per item: 28 x 12
 constexpr int NOUT = OH * OW;                 // 336
 constexpr int A_BYTES = kTileM * 128;         // 16 KB per hi / lo tile
 constexpr int STAGE_BYTES = 2 * A_BYTES;
-constexpr int STAGES = 5;
+constexpr int STAGES = 4;
 constexpr int W_TILE = NT * 128;              // 4 KB: [32 taps][64 ci] fp16
 constexpr int W_SET = 2 * W_TILE;             // [W_hi | W_lo]
 constexpr int SLOT_COLS = 2 * NT, SLOTS = 8, TMEM_COLS = 512;
 constexpr int W_OFF = STAGES * STAGE_BYTES;
-constexpr int RESP_OFF = W_OFF + 2 * W_SET;                   // float [2 buffers][25][128]
-constexpr int RGB_OFF = RESP_OFF + 2 * 25 * 128 * 4;          // uint8 [28][36]
-constexpr int BAR_OFF = (RGB_OFF + OH * OW * 3 + 15) / 16 * 16;
+constexpr int RESP_OFF = W_OFF + 2 * W_SET;                   // float [team][2 buffers][25][128]
+constexpr int RESP_TEAM = 2 * 25 * 128 * 4;
+constexpr int RGB_OFF = RESP_OFF + kTeams * RESP_TEAM;        // uint8 [team][28][36]
+constexpr int RGB_TEAM = (OH * OW * 3 + 15) / 16 * 16;
+constexpr int BAR_OFF = RGB_OFF + kTeams * RGB_TEAM;
 constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -49,8 +53,6 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + W_OFF;                               // [set][W_hi | W_lo]
-  float (*resp_s)[128] = reinterpret_cast<float (*)[128]>(smem + RESP_OFF);
-  uint8_t* rgb_s = smem + RGB_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
@@ -146,18 +148,25 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     // responses at compile-time offsets.  The three planes' outputs stay in registers until the colour step.
     const int lg = warp & 3;
     const int q = lg * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;    // 0..127 among the epilogue threads
+    const int team = (warp - 2) >> 2;
+    const int et = ((warp - 2) & 3) * 32 + lane;    // 0..127 among the team's threads
+    float (*resp_s)[128] = reinterpret_cast<float (*)[128]>(smem + RESP_OFF + team * RESP_TEAM);
+    uint8_t* rgb_s = smem + RGB_OFF + team * RGB_TEAM;
     const int r = q >> 3, c = q & 7;
     const bool interior = r >= 1 && r <= IH && c >= 1 && c <= IW;
-    int slot = 0; uint32_t slot_phase = 0;
     int rbuf = 0;
-    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    int k_item = 0;                            // this CTA's item counter: item k uses TMEM slots 3k .. 3k+2 (mod SLOTS)
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++k_item) {
+      if ((k_item & (kTeams - 1)) != team) continue;
       const int txy = it % tiles_per_image, n = it / tiles_per_image;
       const int ty = txy / tiles_x, tx = txy % tiles_x;
       float outv[3][4];                        // [plane][py*2+px]
 #pragma unroll
       for (int plane = 0; plane < 3; ++plane) {
         const int set = plane == 0 ? 0 : 1;
+        const int cnt = 3 * k_item + plane;
+        const int slot = cnt & (SLOTS - 1);
+        const uint32_t slot_phase = (cnt / SLOTS) & 1;
         mbar_wait(&slot_full[slot], slot_phase, error_flag, 5);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS;
@@ -168,13 +177,12 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
-        if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
-        const float inv_scale = prm.inv_scale[set];
+        const float inv_scale = prm.inv_scale[set];       // a power of two: scaling the gathered sum is bit-identical to scaling its terms
         float (*resp)[128] = resp_s + rbuf * 25;
 #pragma unroll
         for (int t = 0; t < 25; ++t)
-          resp[t][q] = __fadd_rn(__uint_as_float(vm[t]), __uint_as_float(vc[t])) * inv_scale;
-        epi_barrier();                         // also orders the previous use of the other buffer (see below)
+          resp[t][q] = __fadd_rn(__uint_as_float(vm[t]), __uint_as_float(vc[t]));
+        epi_barrier(team);                     // also orders the previous use of the other buffer (see below)
         if (interior) {
           const float bias = prm.bias[set];
 #pragma unroll
@@ -189,7 +197,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 for (int tb = (px + 1) & 1; tb < 5; tb += 2)
                   acc = __fadd_rn(acc, resp[ta * 5 + tb][q + ((py + 1 - ta) / 2) * kTileCols + (px + 1 - tb) / 2]);
               }
-              const float v = leaky(__fadd_rn(acc, bias));
+              const float v = leaky(__fadd_rn(__fmul_rn(acc, inv_scale), bias));
               outv[plane][py * 2 + px] = fminf(fmaxf(v, 0.0f), 1.0f);      // decoder.py:32
             }
           }
@@ -230,7 +238,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int k = 0; k < 3; ++k) rgb_s[ry * (OW * 3) + rx * 3 + k] = (uint8_t)rintf(__fmul_rn(ch[k], 255.0f));   // decoder.py:48
         }
       }
-      epi_barrier();
+      epi_barrier(team);
       if (prm.rgb) {
         constexpr int ROWB = OW * 3;                            // 36 bytes per tile row
         const bool vec4 = (ox0 + OW <= Wo) && (Wo % 4 == 0);
@@ -250,7 +258,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
         }
       }
-      epi_barrier();                         // rgb_s is free for the next item
+      epi_barrier(team);                     // rgb_s is free for the next item
     }
   }
 
