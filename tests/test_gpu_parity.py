@@ -269,6 +269,56 @@ def test_config2_kodak_batch(nn, codec_factory):
     _cross_check(nn, codec_factory, synthetic_images(24, 512, 768, seed=2))
 
 
+def config2_batch():
+    """image 0 = kodim21; images 1-11 = flips and 8-pixel-multiple cyclic shifts of it; images 12-23 =
+    mosaics (4 x 6 tiles of 128 x 128) of the golden ImageNet patches with per-tile flips.  Fixed recipe, seed 0."""
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    k = np.array(Image.open(os.path.join(GOLDEN, "kodim21.png")))
+    patches = load_golden("imagenet_patches")["input"]
+    rng = np.random.default_rng(0)
+    imgs = [k, k[::-1], k[:, ::-1], k[::-1, ::-1]]
+    while len(imgs) < 12:
+        dy, dx = 8 * int(rng.integers(1, 64)), 8 * int(rng.integers(1, 96))
+        imgs.append(np.roll(imgs[len(imgs) % 4], (dy, dx), axis=(0, 1)))
+    while len(imgs) < 24:
+        m = np.empty((512, 768, 3), np.uint8)
+        for ty in range(4):
+            for tx in range(6):
+                t = patches[int(rng.integers(0, patches.shape[0]))]
+                if rng.integers(0, 2):
+                    t = t[::-1]
+                if rng.integers(0, 2):
+                    t = t[:, ::-1]
+                m[128 * ty:128 * ty + 128, 128 * tx:128 * tx + 128] = t
+        imgs.append(m)
+    return np.ascontiguousarray(np.stack(imgs))
+
+
+def test_config2_recipe_against_oracle(nn, codec_factory):
+    """BASELINE.json config 2 at full size (24 x 768x512) against the oracle itself: symbols (ties only), histograms,
+    bpp and reconstruction PSNR, through the fused encode + rate call and the decoder."""
+    img = config2_batch()
+    assert img.shape == (24, 512, 768, 3)
+    eY, eC, dY, dC = make_weights("spread")
+    enc, dec = codec_factory("spread", "tc_split")
+    sym, r = enc.encode_rate(img)
+    pre64 = O.encode_prequant(img, eY, eC, "f64")
+    sym64 = O.quantise(pre64)
+    tie = np.abs(pre64 * 255.0 - np.floor(pre64 * 255.0) - 0.5)
+    check_symbols(sym, sym64, tie)
+    hist, ent, bpp, hg = O.rate(sym, 512, 768)
+    assert np.array_equal(r.hist.astype(np.int64), hist)
+    assert np.array_equal(r.hist_global.astype(np.int64), hg)
+    assert np.abs(r.bpp - O.rate(sym64, 512, 768)[2]).max() < BPP_TOL
+    rec = dec(sym64)
+    rec_ref = O.decode(sym64, dY, dC, "f32")
+    check_symbols(rec, rec_ref)
+    for i in range(24):
+        assert abs(O.psnr(img[i], rec[i]) - O.psnr(img[i], rec_ref[i])) < PSNR_TOL_DB
+
+
 def test_config3_patch_batch(nn, codec_factory):
     """ImageNet-patch shape, a 512-patch slice of the 4096 x 128x128 config: encode + rate."""
     _cross_check(nn, codec_factory, synthetic_images(512, 128, 128, seed=3), check_decode=False)
