@@ -118,6 +118,14 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
 int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, uint32_t* hist,
                      float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream);
 
+/* Cross-rank sum of the global symbol counts: the path's only exchange step.
+ *   nccl_comm    the caller's ncclComm_t for this rank (one rank per GPU)
+ *   hist_global  DEVICE uint64 [3][256], summed in place over all ranks of the communicator
+ * Enqueues one ncclAllReduce(sum, uint64, 768) on `stream`.  NCCL is resolved at call time from the library the
+ * process has already loaded (so the communicator and the call come from the same NCCL), else from libnccl.so.2;
+ * libnnic.so has no link-time dependency on it.  Integer sums: the result is identical for any number of ranks. */
+int nnic_hist_allreduce(nnic_t* h, void* nccl_comm, uint64_t* hist_global, void* stream);
+
 /* Entropy of already-reduced counts (e.g. hist_global after the cross-rank allreduce):
  *   counts uint64 [rows][256] -> entropy_bits float [rows].  Same formula as nnic_rate. */
 int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits,

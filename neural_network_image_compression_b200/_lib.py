@@ -33,6 +33,7 @@ SYMBOLS = (
     ("nnic_run_decoder_planes", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp)),
     ("nnic_encode_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp)),
+    ("nnic_hist_allreduce", C.c_int, (_vp, _vp, _vp, _vp)),
     ("nnic_entropy_from_counts", C.c_int, (_vp, _vp, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_set_micro_batch", C.c_int, (_vp, C.c_int)),
     ("nnic_scratch_bytes", C.c_size_t, (_vp,)),

@@ -1,6 +1,7 @@
 // C ABI of libnnic.so (see include/nnic.h): handle, weight repacking, scratch arena, and the
 // layer-by-layer orchestration of the encode / decode / rate paths.
 #include <cuda.h>
+#include <dlfcn.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -1088,6 +1089,27 @@ int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t
   if (int rc = rate_setup(h, N, 0, hist, entropy_bits, bpp, hist_global, host, st, rb)) return rc;
   if (int rc = encode_impl(h, rgb, N, H, W, latent, nullptr, rb.d_hist, mem_kind, stream)) return rc;
   return rate_finish(h, N, (H + 7) / 8, (W + 7) / 8, H, W, hist, entropy_bits, bpp, hist_global, host, st, rb);
+}
+
+int nnic_hist_allreduce(nnic_t* h, void* nccl_comm, uint64_t* hist_global, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!nccl_comm || !hist_global) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_hist_allreduce: NULL communicator or buffer");
+  // int ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = nullptr;
+  if (!fn) {
+    fn = (allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!fn) {
+      void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (lib) fn = (allreduce_fn)dlsym(lib, "ncclAllReduce");
+    }
+    if (!fn) return fail(h, NNIC_ERR_CUDA, "nnic_hist_allreduce: NCCL (libnccl.so.2) is not available in this process");
+  }
+  DeviceGuard g(h->device);
+  constexpr int kNcclUint64 = 5, kNcclSum = 0;       // nccl.h: ncclDataType_t / ncclRedOp_t
+  const int rc = fn(hist_global, hist_global, 768, kNcclUint64, kNcclSum, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return fail(h, NNIC_ERR_CUDA, "ncclAllReduce failed with ncclResult_t %d", rc);
+  return NNIC_OK;
 }
 
 int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits, int mem_kind, void* stream) {

@@ -33,3 +33,40 @@ def test_nccl_histogram_allreduce_and_global_rate(nn, codec_factory):
         assert np.abs(e - O.entropy_from_hist(want)).max() < 1e-5
     finally:
         dist.destroy_process_group()
+
+
+def test_c_abi_hist_allreduce_over_nccl(nn):
+    """nnic_hist_allreduce (include/nnic.h): the exchange step through the C ABI with the caller's ncclComm_t.  One
+    process drives every visible GPU (up to 2) with communicators from ncclCommInitAll; on a one-GPU box the
+    communicator has one rank and the sum is the identity."""
+    import ctypes as C
+    import torch
+    ndev = min(torch.cuda.device_count(), 2)
+    nccl = C.CDLL("libnccl.so.2", mode=C.RTLD_GLOBAL)
+    comms = (C.c_void_p * ndev)()
+    devs = (C.c_int * ndev)(*range(ndev))
+    assert nccl.ncclCommInitAll(comms, ndev, devs) == 0
+    try:
+        rng = np.random.default_rng(2)
+        lats = [np.minimum(rng.geometric(0.15, size=(3, 8, 12, 96)) - 1, 255).astype(np.uint8) for _ in range(ndev)]
+        handles = [nn.Handle(d) for d in range(ndev)]
+        hgs = []
+        for d in range(ndev):
+            with torch.cuda.device(d):
+                r = nn.rate(handles[d], torch.from_numpy(lats[d]).cuda(d), 64, 96)
+                hgs.append(r.hist_global)
+                torch.cuda.synchronize(d)
+        assert nccl.ncclGroupStart() == 0
+        for d in range(ndev):
+            h = handles[d]
+            h.check(h.lib.nnic_hist_allreduce(h.h, comms[d], hgs[d].data_ptr(), None), "nnic_hist_allreduce")
+        assert nccl.ncclGroupEnd() == 0
+        want = sum(O.histogram(lat).sum(axis=0) for lat in lats)
+        for d in range(ndev):
+            torch.cuda.synchronize(d)
+            assert np.array_equal(hgs[d].cpu().numpy(), want)
+        with pytest.raises(nn.NnicError):
+            handles[0].check(handles[0].lib.nnic_hist_allreduce(handles[0].h, None, hgs[0].data_ptr(), None), "null comm")
+    finally:
+        for d in range(ndev):
+            nccl.ncclCommDestroy(C.c_void_p(comms[d]))
