@@ -339,6 +339,48 @@ def main():
                         "frac": round(ach / peaks["tflops"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"],
                         "note": "algorithmic FLOPs; the fp16 hi/lo split issues 3x as many tensor-core FLOPs"}
 
+    # ---- informational: the same steps with the optional fp16 decoder arithmetic (NOT the headline: `value` and `e2e`
+    #      above use the decoder that is as exact as the encoder) ----
+    decode_fp16 = None
+    if "decode" in stages and args.arith == "tc_split":
+        dec16 = nn.Decoder(local, args.arith, precision="fp16")
+        for i in range(2):
+            dec16.set_weights(i, dec.weights[i])
+        rgb16 = torch.empty_like(rgb_buf)
+        dec_exact = dec
+
+        def step16(i):
+            x = inputs[i % n_sets]
+            lat = x
+            if "encode" in stages:
+                lat = enc(x, out=lat_buf)
+            dec16(lat, out=rgb16)
+            return lat
+        lat = step16(0)
+        dec_exact(lat, out=rgb_buf)
+        torch.cuda.synchronize()
+        diff = (rgb16.to(torch.int16) - rgb_buf.to(torch.int16)).abs()
+        frac, dmax = float((diff != 0).float().mean().item()), int(diff.max().item())
+        for i in range(warmup):
+            step16(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k16 = max(3, min(args.steps, 50))
+        f0.record()
+        for i in range(k16):
+            step16(warmup + i)
+        f1.record()
+        barrier()
+        ms16 = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms16], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms16 = float(t.item())
+        decode_fp16 = {"value": round(mp_per_step * k16 / (ms16 / 1e3), 2), "unit": "MP/s", "ms_per_step": round(ms16 / k16, 4),
+                       "steps": k16, "stages": [s_ for s_ in stages if s_ != "rate"],
+                       "differing_bytes_frac": round(frac, 5), "max_abs_byte_diff": dmax,
+                       "note": "Decoder(precision='fp16'): one fp16 product per MAC; within BASELINE's 0.01 dB PSNR, not byte-identical"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         sample = max(1, min(n_img, int(round(2.4e6 / (H * W))) or 1))
@@ -358,6 +400,8 @@ def main():
                    "steps": e2e_steps, "api": "Encoder().encode_rate(x) / Decoder()(x) on pinned NumPy buffers"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
            "cpu_baseline": cpu_baseline}
+    if decode_fp16:
+        out["decode_fp16"] = decode_fp16
     emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()

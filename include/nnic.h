@@ -54,6 +54,15 @@ enum { NNIC_LAYERS_PER_NET = 5 };
  * conv1, dconv8, colour, quantise, histogram and pack kernels are fp32/integer in both modes. */
 enum nnic_arith { NNIC_ARITH_TC_SPLIT = 0, NNIC_ARITH_SIMT_F32 = 1 };
 
+/* Optional reduced precision of the DECODER under NNIC_ARITH_TC_SPLIT (the encoder is never affected: its symbols
+ * must be bit-exact).  BASELINE.json asks reconstructions to be within 0.01 dB PSNR of the reference, not bit-exact:
+ *   NNIC_DECODE_SPLIT  default: as exact as the encoder (0 differing bytes against the fp32 restatement in the tests)
+ *   NNIC_DECODE_FP16   dconv1..dconv7: ONE fp16 product per MAC (activations and weights rounded to fp16, fp32
+ *                      accumulation in TMEM, activations stored as one fp16 plane); dconv8: A_hi x (W_hi + W_lo).
+ *                      About 1/3 of the tensor work and 1/2 of the activation traffic; reconstruction bytes differ
+ *                      from the exact decoder by +-1 in a few per cent of the positions (tests state the PSNR bound). */
+enum nnic_decode_precision { NNIC_DECODE_SPLIT = 0, NNIC_DECODE_FP16 = 1 };
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 
 /* Replaces: constructing Encoder()/Decoder() (encoder.py:34-36, decoder.py:35-37). */
@@ -63,6 +72,8 @@ const char* nnic_last_error(const nnic_t* h);   /* never NULL; h may be NULL (gl
 const char* nnic_version(void);
 int nnic_set_arith(nnic_t* h, int arith);
 int nnic_get_arith(const nnic_t* h);
+int nnic_set_decode_precision(nnic_t* h, int precision);
+int nnic_get_decode_precision(const nnic_t* h);
 /* Number of kernel launches this handle has enqueued since creation (bench.py's gpu_launches). */
 uint64_t nnic_launch_count(const nnic_t* h);
 

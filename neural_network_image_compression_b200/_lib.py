@@ -34,6 +34,8 @@ SYMBOLS = (
     ("nnic_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp)),
     ("nnic_encode_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp)),
     ("nnic_hist_allreduce", C.c_int, (_vp, _vp, _vp, _vp)),
+    ("nnic_set_decode_precision", C.c_int, (_vp, C.c_int)),
+    ("nnic_get_decode_precision", C.c_int, (_vp,)),
     ("nnic_entropy_from_counts", C.c_int, (_vp, _vp, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_set_micro_batch", C.c_int, (_vp, C.c_int)),
     ("nnic_scratch_bytes", C.c_size_t, (_vp,)),
@@ -115,6 +117,16 @@ class Handle:
     def set_arith(self, arith):
         code = ARITH_NAMES[arith] if isinstance(arith, str) else int(arith)
         self.check(self.lib.nnic_set_arith(self.h, code), "nnic_set_arith")
+
+    def set_decode_precision(self, precision):
+        """'split' (default, as exact as the encoder) or 'fp16' (one fp16 product per MAC in the decoder; see
+        include/nnic.h enum nnic_decode_precision)."""
+        code = {"split": 0, "fp16": 1}[precision] if isinstance(precision, str) else int(precision)
+        self.check(self.lib.nnic_set_decode_precision(self.h, code), "nnic_set_decode_precision")
+
+    @property
+    def decode_precision(self) -> str:
+        return ("split", "fp16")[self.lib.nnic_get_decode_precision(self.h)]
 
     @property
     def arith(self) -> str:

@@ -92,6 +92,7 @@ struct TcPatchParams {
   int patch_c0[4];
   int seg_steps[4];
   int cout;                   // 64, or 32 (conv8)
+  int fast;                   // one fp16 product per MAC, hi planes only (decoder, nnic_set_decode_precision)
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;
@@ -136,6 +137,7 @@ cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_fl
 // ---- dconv8 + colour inverse + pack on the tensor cores (tc_dconv8.cu) ------------------------------
 struct TcDconv8Params {
   int N, Hi, Wi;              // images, input size (output is 2Hi x 2Wi)
+  int fast;                   // activations as one fp16 plane: A_hi x [W_hi | W_lo] only
   float inv_scale[2];         // 2^-(ka+kw) per weight set
   float bias[2];
   ColourConsts cc;

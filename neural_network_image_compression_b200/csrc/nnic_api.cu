@@ -71,6 +71,7 @@ struct nnic_handle {
   std::string err;
   uint64_t launches = 0;
   int micro_batch = 0;
+  bool decode_fp16 = false;         // nnic_set_decode_precision: decoder GEMM layers with one fp16 product per MAC
   uint32_t* fused_hist = nullptr;   // set around conv8's launch by encode_batch: device [nb][3][256] counts to add to
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   EncodeTiledFn encode_tiled = nullptr;
@@ -568,6 +569,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.res_hi = res ? res->hi : nullptr; pp.res_lo = res ? res->lo : nullptr;
     pp.out_mode = out_mode;
     pp.cout = L.cout;
+    pp.fast = (net == 1 && h->decode_fp16) ? 1 : 0;
     pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
     pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
     pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
@@ -700,6 +702,7 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
     TcDconv8Params dp;
     memset(&dp, 0, sizeof dp);
     dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
+    dp.fast = h->decode_fp16 ? 1 : 0;
     dp.inv_scale[0] = h->d8_inv_scale[0]; dp.inv_scale[1] = h->d8_inv_scale[1];
     dp.bias[0] = h->b_edge[1][0]; dp.bias[1] = h->b_edge[1][1];
     dp.cc = colour_consts();
@@ -807,6 +810,15 @@ int nnic_set_arith(nnic_t* h, int arith) {
   h->arith = arith;
   return NNIC_OK;
 }
+int nnic_set_decode_precision(nnic_t* h, int precision) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (precision != NNIC_DECODE_SPLIT && precision != NNIC_DECODE_FP16)
+    return fail(h, NNIC_ERR_INVALID_ARG, "nnic_set_decode_precision: unknown precision %d", precision);
+  h->decode_fp16 = precision == NNIC_DECODE_FP16;
+  return NNIC_OK;
+}
+int nnic_get_decode_precision(const nnic_t* h) { return h && h->decode_fp16 ? NNIC_DECODE_FP16 : NNIC_DECODE_SPLIT; }
+
 int nnic_get_arith(const nnic_t* h) { return h ? h->arith : NNIC_ERR_INVALID_ARG; }
 uint64_t nnic_launch_count(const nnic_t* h) { return h ? h->launches : 0; }
 int nnic_set_micro_batch(nnic_t* h, int n) { if (!h || n < 0) return NNIC_ERR_INVALID_ARG; h->micro_batch = n; return NNIC_OK; }

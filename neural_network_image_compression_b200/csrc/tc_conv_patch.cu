@@ -73,7 +73,9 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int RB, int NSPLIT, int COUT>
+// FAST: one fp16 product per MAC (A_hi x W_hi only, activations written as one fp16 plane) -- the decoder's optional
+// reduced-precision arithmetic (nnic_set_decode_precision); the lo planes are neither read nor written.
+template <int RB, int NSPLIT, int COUT, bool FAST>
 __global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -135,9 +137,9 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (prm.dbg & 16) {
             mbar_arrive(&patch_full[pb]);
           } else {
-            mbar_expect_tx(&patch_full[pb], 2 * PATCH_TX);
+            mbar_expect_tx(&patch_full[pb], FAST ? PATCH_TX : 2 * PATCH_TX);
             tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
-            tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
+            if (!FAST) tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
           }
         }
         __syncwarp();
@@ -165,10 +167,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (prm.dbg & 4) {
               mbar_arrive(&w_full[ws]);
             } else {
-              mbar_expect_tx(&w_full[ws], W_SLOT);
+              mbar_expect_tx(&w_full[ws], FAST ? W_TILE : W_SLOT);
               const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s0].w_row;
               tma_load_2d(&map_w_hi, wb, &w_full[ws], 0, wrow);
-              tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
+              if (!FAST) tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
             }
           }
           __syncwarp();
@@ -228,8 +230,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                   for (int ks = 0; ks < KSTEPS; ++ks) {
                     if (ks >= ks_begin) {
-                      umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, accumulate);
-                      umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                      if (FAST) {
+                        umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_narrow, accumulate);
+                      } else {
+                        umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, accumulate);
+                        umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                      }
                       accumulate = 1u;
                     }
                   }
@@ -286,7 +292,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           for (int q = 0; q < HALF / 16; ++q) {
             if (valid) {
               ld_global_v8(prm.res_hi + ooff + 16 * q, res_h + 8 * q);
-              ld_global_v8(prm.res_lo + ooff + 16 * q, res_l + 8 * q);
+              if (!FAST) ld_global_v8(prm.res_lo + ooff + 16 * q, res_l + 8 * q);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) { res_h[8 * q + e] = 0; res_l[8 * q + e] = 0; }
@@ -300,14 +306,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
           uint32_t vm[HALF], vc[HALF];
-          if (HALF == 32) { tmem_ld32_nowait(taddr, vm); tmem_ld32_nowait(taddr + COUT, vc); }
-          else { tmem_ld16_nowait(taddr, vm); tmem_ld16_nowait(taddr + COUT, vc); }
+          if (HALF == 32) { tmem_ld32_nowait(taddr, vm); if (!FAST) tmem_ld32_nowait(taddr + COUT, vc); }
+          else { tmem_ld16_nowait(taddr, vm); if (!FAST) tmem_ld16_nowait(taddr + COUT, vc); }
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_empty[slot]);
 #pragma unroll
-          for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
+          for (int i = 0; i < HALF; ++i)
+            acc[i] = __fadd_rn(acc[i], FAST ? __uint_as_float(vm[i]) : __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
           t_ld += TICK() - te1;
         }
@@ -323,7 +330,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const __half* rh = reinterpret_cast<const __half*>(res_h);
             const __half* rl = reinterpret_cast<const __half*>(res_l);
 #pragma unroll
-            for (int i = 0; i < HALF; ++i) acc[i] = __fadd_rn(acc[i], join_f32(rh[i], rl[i]));
+            for (int i = 0; i < HALF; ++i)
+              acc[i] = __fadd_rn(acc[i], FAST ? __half2float(rh[i]) * ACT_INV_SCALE : join_f32(rh[i], rl[i]));
           }
           if (COUT == 32 && prm.clamp01) {
 #pragma unroll
@@ -337,7 +345,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {
                 st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
-                st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
+                if (!FAST) st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
               }
             }
           } else if (prm.out_mode == TC_OUT_F32) {
@@ -412,13 +420,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT, int COUT>
+template <int RB, int NSPLIT, int COUT, bool FAST = false>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT, COUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -426,7 +434,7 @@ static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap&
   const long long items = (long long)tiles_x * tiles_y * prm.P;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_conv_patch<RB, NSPLIT, COUT><<<grid, PCfg<RB, NSPLIT, COUT>::kThreads, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
+  k_tc_conv_patch<RB, NSPLIT, COUT, FAST><<<grid, PCfg<RB, NSPLIT, COUT>::kThreads, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
   return cudaGetLastError();
 }
 
@@ -435,6 +443,13 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
                                  cudaStream_t stream) {
   // layers whose epilogue is the limiter (residual add, or several output phases per work item) use 16 epilogue warps
   const bool heavy_epilogue = prm.res_hi != nullptr || prm.njobs > 1;
+  if (prm.fast) {
+    if (prm.cout != 64 || prm.out_mode != TC_OUT_SPLIT) return cudaErrorInvalidValue;
+    if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    if (row_bytes == 128) return launch_patch_impl<128, 2, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    if (row_bytes == 64) return launch_patch_impl<64, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    return cudaErrorInvalidValue;
+  }
   if (row_bytes == 128 && prm.cout == 32) return launch_patch_impl<128, 2, 32>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   if (row_bytes == 128) return launch_patch_impl<128, 2, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);

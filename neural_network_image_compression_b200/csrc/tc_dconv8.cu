@@ -102,9 +102,9 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);
         if (elect_one()) {
           uint8_t* sb = stage_base + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], prm.fast ? A_BYTES : STAGE_BYTES);
           tma_load_5d(&map_a_hi, sb, &full_bar[stage], 0, X0, 0, Y0, plane * N + n);
-          tma_load_5d(&map_a_lo, sb + A_BYTES, &full_bar[stage], 0, X0, 0, Y0, plane * N + n);
+          if (!prm.fast) tma_load_5d(&map_a_lo, sb + A_BYTES, &full_bar[stage], 0, X0, 0, Y0, plane * N + n);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -130,8 +130,8 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, ks ? 1u : 0u);
-            umma_f16(d_tmem + NT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+            umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, ks ? 1u : 0u);     // A_hi x [W_hi | W_lo]
+            if (!prm.fast) umma_f16(d_tmem + NT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
           }
           umma_commit(&empty_bar[stage]);
           umma_commit(&slot_full[slot]);

@@ -10,6 +10,13 @@ from .utils import ProClass, _is_torch, _stream_of
 class Decoder(ProClass):
     kind = "decoder"
 
+    def __init__(self, device: int = 0, arith: str = "tc_split", handle=None, precision: str = "split"):
+        """precision='fp16' selects the optional reduced-precision decoder arithmetic (one fp16 product per MAC;
+        reconstructions stay within BASELINE.json's 0.01 dB PSNR of the exact decoder but are not byte-identical)."""
+        super().__init__(device, arith, handle)
+        if precision != "split":
+            self.handle.set_decode_precision(precision)
+
     def __call__(self, x, return_prequant: bool = False, out=None):
         """decoder.py:39-48.  x: uint8 [N,h,w,96] latent -> uint8 [N,8h,8w,3] RGB (not cropped to the
         source size, like the reference).  NumPy in -> NumPy out through host buffers; CUDA torch

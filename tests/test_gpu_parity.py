@@ -410,3 +410,40 @@ def test_outputs_stay_inside_their_buffers(nn, codec_factory, shape):
     assert np.array_equal(lat.cpu().numpy(), want_lat)
     assert np.array_equal(rgb.cpu().numpy(), dec(want_lat))
     assert np.array_equal(np.round(pre.view(n, lh, lw, 96).cpu().numpy() * np.float32(255)).astype(np.uint8), want_lat)
+
+
+@pytest.mark.parametrize("wname", ["default", "spread"])
+def test_fp16_decoder_meets_the_reconstruction_tolerance(nn, wname):
+    """Optional decoder arithmetic NNIC_DECODE_FP16 (one fp16 product per MAC): not byte-identical, but inside
+    BASELINE.json's reconstruction criterion -- PSNR against the source within 0.01 dB of the reference decoder's, every
+    differing byte +-1 -- on kodim21 (config 1), the golden crops and a ragged-tile size; the exact decoder on the same
+    handle type is unaffected, and the encoder ignores the setting."""
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    eY, eC, dY, dC = make_weights(wname)
+    enc = nn.Encoder(0)
+    enc.set_weights(0, eY); enc.set_weights(1, eC)
+    dec_exact, dec_fast = nn.Decoder(0), nn.Decoder(0, precision="fp16")
+    assert dec_fast.handle.decode_precision == "fp16" and dec_exact.handle.decode_precision == "split"
+    for d in (dec_exact, dec_fast):
+        d.set_weights(0, dY); d.set_weights(1, dC)
+    kodim = np.array(Image.open(os.path.join(GOLDEN, "kodim21.png")))[None]
+    for img in (kodim, load_golden("imagenet_patches")["input"], synthetic_images(3, 72, 40, seed=51)):
+        sym = enc(img)
+        rec_ref = O.decode(sym, dY, dC, "f32")
+        rec_exact, rec_fast = dec_exact(sym), dec_fast(sym)
+        check_symbols(rec_exact, rec_ref)
+        d = rec_fast.astype(int) - rec_ref.astype(int)
+        assert np.abs(d).max() <= 1
+        assert (d != 0).mean() < 0.12
+        for i in range(img.shape[0]):
+            assert abs(O.psnr(img[i], rec_fast[i]) - O.psnr(img[i], rec_ref[i])) < PSNR_TOL_DB
+            assert O.psnr(rec_ref[i], rec_fast[i]) > 55.0
+    # the encoder of a handle set to fp16 decoding still produces the exact symbols
+    enc2 = nn.Encoder(0)
+    enc2.handle.set_decode_precision("fp16")
+    enc2.set_weights(0, eY); enc2.set_weights(1, eC)
+    assert np.array_equal(enc2(kodim), enc(kodim))
+    with pytest.raises(nn.NnicError):
+        dec_fast.handle.set_decode_precision(7)
