@@ -49,7 +49,9 @@ enum { NNIC_LAYERS_PER_NET = 5 };
 
 /* Arithmetic of the eight GEMM-shaped layers (conv2/3/4/8, dconv1/5/6/7):
  *   NNIC_ARITH_TC_SPLIT  tcgen05 tensor cores, fp16 hi+lo split operands (3 MMAs per product),
- *                        fp32 accumulation in TMEM.  Default.  Needs H and W multiples of 8.
+ *                        fp32 accumulation in TMEM.  Default.  Image sizes that are not multiples of 8 (the
+ *                        parity views of the stride-2 layers need even sizes at every stage) are encoded by the
+ *                        NNIC_ARITH_SIMT_F32 kernels for that call -- on the GPU, within the same tolerance.
  *   NNIC_ARITH_SIMT_F32  plain fp32 FFMA kernels (any H, W >= 1).  Cross-check path.
  * conv1, dconv8, colour, quantise, histogram and pack kernels are fp32/integer in both modes. */
 enum nnic_arith { NNIC_ARITH_TC_SPLIT = 0, NNIC_ARITH_SIMT_F32 = 1 };

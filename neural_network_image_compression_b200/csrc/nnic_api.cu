@@ -727,11 +727,17 @@ size_t dec_act_need(bool split, size_t P, int lh, int lw) {
   return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
 }
 
-int check_tc_shape(nnic_t* h, int H, int W) {
-  if (h->arith == NNIC_ARITH_TC_SPLIT && (H % 8 != 0 || W % 8 != 0))
-    return fail(h, NNIC_ERR_SHAPE, "tensor-core arithmetic needs H and W to be multiples of 8 (got %dx%d); use NNIC_ARITH_SIMT_F32", H, W);
-  return 0;
-}
+// The tensor-core kernels read stride-2 inputs through parity views, which need even sizes at every stage, i.e. H and W
+// multiples of 8.  Other sizes (TF SAME padding then pads (2,2) instead of (1,2)) run the same call through the fp32 FFMA
+// kernels -- still on the GPU, same results within the parity tolerance, several times slower.  The guard restores the
+// handle's arithmetic when the call returns.
+struct ArithForShape {
+  nnic_t* h; int saved;
+  ArithForShape(nnic_t* h_, int H, int W) : h(h_), saved(h_->arith) {
+    if (h->arith == NNIC_ARITH_TC_SPLIT && (H % 8 != 0 || W % 8 != 0)) h->arith = NNIC_ARITH_SIMT_F32;
+  }
+  ~ArithForShape() { h->arith = saved; }
+};
 
 }  // namespace
 
@@ -851,7 +857,7 @@ static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8
   if (!rgb || !latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: non-positive shape %dx%dx%d", N, H, W);
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
-  if (int rc = check_tc_shape(h, H, W)) return rc;
+  ArithForShape arith_guard(h, H, W);
   DeviceGuard g(h->device);
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -966,7 +972,7 @@ int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W,
   if (!h) return NNIC_ERR_INVALID_ARG;
   if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_encoder_planes: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
-  if (int rc = check_tc_shape(h, H, W)) return rc;
+  ArithForShape arith_guard(h, H, W);
   DeviceGuard g(h->device);
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;

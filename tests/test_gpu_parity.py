@@ -102,8 +102,9 @@ def test_small_and_ragged_tiles(codec_factory, shape):
 
 @pytest.mark.parametrize("shape", [(1, 20, 13), (2, 7, 9), (1, 1, 1), (1, 33, 50)])
 def test_sizes_not_multiple_of_8_use_ffma_path(nn, codec_factory, shape):
-    """TF SAME padding for odd sizes ((2,2) instead of (1,2)), ceil at each stride: only the FFMA arithmetic
-    accepts these; the tensor-core arithmetic refuses them loudly."""
+    """TF SAME padding for odd sizes ((2,2) instead of (1,2)), ceil at each stride.  The tensor-core kernels need
+    multiples of 8; a handle in tensor-core mode runs such a call through the FFMA kernels by itself (same bytes as an
+    explicit simt_f32 handle) and goes back to the tensor cores for the next call."""
     n, h, w = shape
     img = synthetic_images(n, h, w, seed=7)
     eY, eC, dY, dC = make_weights("spread")
@@ -114,9 +115,13 @@ def test_sizes_not_multiple_of_8_use_ffma_path(nn, codec_factory, shape):
     check_symbols(sym, want)
     rec = dec(sym)
     check_symbols(rec, O.decode(sym, dY, dC, "f64"))
-    enc_tc, _ = codec_factory("spread", "tc_split")
-    with pytest.raises(nn.NnicError):
-        enc_tc(img)
+    enc_tc, dec_tc = codec_factory("spread", "tc_split")
+    sym_tc, r = enc_tc.encode_rate(img)
+    assert np.array_equal(sym_tc, sym) and enc_tc.handle.arith == "tc_split"
+    assert np.array_equal(r.hist.astype(np.int64), O.histogram(sym))
+    check_symbols(dec_tc(sym), rec)
+    img8 = synthetic_images(1, 16, 24, seed=8)
+    check_symbols(enc_tc(img8), O.encode(img8, eY, eC, "f32"))
 
 
 def test_micro_batches_and_device_api_are_equivalent(nn, codec_factory):
