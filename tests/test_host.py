@@ -11,6 +11,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "neural_network_image_compression_b200")
+HEADER = os.path.join(ROOT, "include", "nnic.h")
+LIB = os.path.join(PKG, "libnnic.so")
 
 
 def header_functions():
@@ -170,3 +172,22 @@ def test_get_bpp_follows_the_reference_definition(nn):
     pic = np.round(noise[0]).astype(np.uint8).reshape(32, 96)
     assert b1[0, 0] == np.float32(8.0 * nn.container.png_size(pic) / (32 * 96))
     assert np.allclose(nn.get_bpp(noise, tot_pixels_compressed=64 * 96), b1 * (32 * 96) / (64 * 96))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/nnic.h must be usable from C (the drop-in boundary is a C ABI): compile a C99 translation unit that
+    references every entry point and link it against libnnic.so (no compute call is made)."""
+    names = re.findall(r"^\s*(?:int|void|const char\*|uint64_t|size_t|long long)\s+(nnic_\w+)\s*\(", open(HEADER).read(), re.M)
+    assert len(names) >= 20
+    src = tmp_path / "use_nnic.c"
+    src.write_text('#include "nnic.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t fns[] = {'
+                   + ", ".join(f"(fn_t){n}" for n in names)
+                   + '};\n  printf("%s %d\\n", nnic_version(), (int)(sizeof fns / sizeof fns[0]));\n  return 0;\n}\n')
+    exe = tmp_path / "use_nnic"
+    lib_dir = os.path.dirname(LIB)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe),
+           "-L", lib_dir, "-lnnic", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("nnic-b200"), r.stdout + r.stderr
