@@ -62,10 +62,16 @@ class ProClass(DatasetDriver):
     def load(self, path: str):
         """utils.py:26-28: one weight file per network, at path+'Y' and path+'CbCr'.
 
-        The reference stores TensorFlow checkpoints there; this build reads `<path><name>.npz`
-        (see weights.save_npz) holding the same variables in the same layouts."""
+        Accepts what the reference writes there -- a TensorFlow checkpoint `<path><name>.index` +
+        `.data-00000-of-00001` (Keras `save_weights`, read by tfbundle.py without TensorFlow) -- or `<path><name>.npz`
+        (weights.save_npz) holding the same variables in the same layouts."""
+        from . import tfbundle
+        names = [layer[0] for layer in W.layers_of(self.kind)]
         for i, name in enumerate(_MODELS):
             p = path + str(name)
+            if tfbundle.is_bundle(p):
+                self.set_weights(i, tfbundle.keras_weights(p, names))
+                continue
             if not p.endswith(".npz"):
                 p += ".npz"
             if not os.path.exists(p):

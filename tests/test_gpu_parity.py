@@ -452,3 +452,21 @@ def test_fp16_decoder_meets_the_reconstruction_tolerance(nn, wname):
     assert np.array_equal(enc2(kodim), enc(kodim))
     with pytest.raises(nn.NnicError):
         dec_fast.handle.set_decode_precision(7)
+
+
+def test_load_reads_tensorflow_checkpoints(nn, codec_factory, tmp_path):
+    """ProClass.load(path) with `<path>Y.index` / `<path>CbCr.index` present (what the reference's save_weights leaves
+    there) gives the same codec as installing the arrays directly."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from tf_bundle_writer import write_bundle
+    eY, eC, dY, dC = make_weights("spread")
+    for prefix, w in (("encoderY", eY), ("encoderCbCr", eC), ("decoderY", dY), ("decoderCbCr", dC)):
+        write_bundle(str(tmp_path / prefix), {f"{k}/.ATTRIBUTES/VARIABLE_VALUE": v for k, v in w.items()})
+    enc = nn.Encoder(0).load(str(tmp_path / "encoder"))
+    dec = nn.Decoder(0).load(str(tmp_path / "decoder"))
+    enc_ref, dec_ref = codec_factory("spread", "tc_split")
+    img = synthetic_images(2, 32, 48, seed=61)
+    sym = enc(img)
+    assert np.array_equal(sym, enc_ref(img))
+    assert np.array_equal(dec(sym), dec_ref(sym))

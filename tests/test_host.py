@@ -191,3 +191,43 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("nnic-b200"), r.stdout + r.stderr
+
+
+def test_tensorflow_checkpoint_reader(nn, tmp_path):
+    """tfbundle.py reads `<prefix>.index` / `.data-00000-of-00001` (Keras save_weights, utils.py:26-28) without
+    TensorFlow.  Fixtures come from tests/tf_bundle_writer.py (same published layout, many small data blocks, prefix
+    compressed keys, CRCs); both variable-naming styles; corruption is detected."""
+    from tf_bundle_writer import write_bundle
+    from neural_network_image_compression_b200 import tfbundle, weights as Wt
+    for kind, style in (("encoder", "attr"), ("decoder", "indexed")):
+        w = Wt.glorot_uniform(kind, 3, 1.3, 0.05)
+        names = [layer[0] for layer in Wt.layers_of(kind)]
+        tensors = {}
+        for i, name in enumerate(names):
+            base = name if style == "attr" else f"layer_with_weights-{i}"
+            for var in ("kernel", "bias"):
+                tensors[f"{base}/{var}/.ATTRIBUTES/VARIABLE_VALUE"] = w[f"{name}/{var}"]
+        tensors["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"] = np.array(7, np.int64)       # unrelated entries are ignored
+        prefix = str(tmp_path / f"{kind}Y")
+        write_bundle(prefix, tensors, block_bytes=120)
+        idx = tfbundle.read_index(prefix + ".index")
+        assert list(idx) == sorted(idx) and "" in idx and "_CHECKPOINTABLE_OBJECT_GRAPH" in idx
+        got = tfbundle.keras_weights(prefix, names)
+        assert set(got) == set(w)
+        for k in w:
+            assert got[k].dtype == np.float32 and np.array_equal(got[k], w[k])
+        Wt.check_weight_set(kind, got)
+    # a flipped byte in the data file is caught by the tensor checksum, one in the index by the block checksum
+    data = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(data, "rb").read()); raw[100] ^= 0x40
+    open(data, "wb").write(raw)
+    with pytest.raises(ValueError, match="checksum"):
+        tfbundle.read_bundle(prefix)
+    raw = bytearray(open(prefix + ".index", "rb").read()); raw[20] ^= 0x01
+    open(prefix + ".index", "wb").write(raw)
+    with pytest.raises(ValueError):
+        tfbundle.read_index(prefix + ".index")
+    with pytest.raises(ValueError, match="magic"):
+        open(str(tmp_path / "bad.index"), "wb").write(b"\\x00" * 64)
+        tfbundle.read_index(str(tmp_path / "bad.index"))
+    assert tfbundle.mask_crc(tfbundle.crc32c(b"123456789")) == (((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF
