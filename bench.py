@@ -30,8 +30,11 @@ WORKLOADS = {
     "c2": (24, 512, 768, ("encode", "rate", "decode"), "Kodak-shape 24x768x512 full encode+entropy estimate+decode"),
     "c3": (4096, 128, 128, ("encode", "rate"), "ImageNet-patch 4096x128x128 encode + rate estimate"),
     "c4": (16, 2160, 3840, ("decode",), "3840x2160 x16 decode-only"),
-    "c5": (8192, 256, 256, ("encode", "rate"), "256x256 patches, 8192 per GPU, encode + histogram allreduce"),
+    "c5": (65536, 256, 256, ("encode", "rate"), "65536 256x256 patches sharded over the GPUs, encode + histogram allreduce"),
 }
+# c5 is BASELINE.json's batch-sharded configuration: the 65536 patches are a FIXED set split over the ranks (strong scaling,
+# SURVEY.md 8d/8e); the other workloads keep a fixed per-GPU batch (weak scaling).
+STRONG = ("c5",)
 
 # algorithmic work per RGB pixel (3 colour planes), SURVEY.md 8a / 8d
 FLOP_PER_PX = {"conv1": 1200, "conv2": 19200, "conv3": 13824, "conv4": 13824, "conv8": 4800, "dconv1": 4800,
@@ -88,6 +91,29 @@ def synthetic_batch_gpu(torch, n, h, w, seed, device):
     up = base.repeat_interleave(8, dim=1).repeat_interleave(8, dim=2)[:, :h, :w].float()
     noise = torch.randn((n, h, w, 3), device=device, generator=g) * 10.0
     return (up + noise).clamp_(0, 255).to(torch.uint8)
+
+
+def sharded_patches_gpu(torch, first, count, h, w, salt, device, chunk=1024):
+    """uint8 RGB patches whose bytes depend only on (global patch index, position, salt), so every sharding of the patch
+    set sees identical data and the all-rank symbol histogram must not depend on the number of GPUs.  Blocky (8x8) base
+    plus uniform noise from an integer hash, generated on the device."""
+    out = torch.empty((count, h, w, 3), dtype=torch.uint8, device=device)
+    yy = torch.arange(h, device=device, dtype=torch.int64).view(1, h, 1, 1)
+    xx = torch.arange(w, device=device, dtype=torch.int64).view(1, 1, w, 1)
+    cc = torch.arange(3, device=device, dtype=torch.int64).view(1, 1, 1, 3)
+
+    def mix(v):
+        v = v & 0xFFFFFFFF
+        v = ((v ^ (v >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+        v = ((v ^ (v >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+        return v ^ (v >> 16)
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        idx = (first + c0 + torch.arange(n, device=device, dtype=torch.int64)).view(n, 1, 1, 1)
+        base = mix(idx * 0x9E3779B1 + (yy // 8) * 0x85EBCA6B + (xx // 8) * 0xC2B2AE35 + cc * 0x27D4EB2F + salt) & 255
+        noise = mix(idx * 0x165667B1 + yy * 0xD3A2646C + xx * 0xFD7046C5 + cc * 0xB55A4F09 + salt + 1) % 41 - 20
+        out[c0:c0 + n] = (base + noise).clamp_(0, 255).to(torch.uint8)
+    return out
 
 
 def synthetic_latent_gpu(torch, n, lh, lw, seed, device):
@@ -187,6 +213,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n_img, H, W, stages, desc = WORKLOADS[args.workload]
+    strong = args.workload in STRONG and not args.per_gpu_images
+    first_img = 0
+    if strong:
+        first_img, last_img = nn.dist.shard_range(n_img, rank, world)      # contiguous slice of the fixed set
+        n_img = last_img - first_img
     if args.per_gpu_images:
         n_img = args.per_gpu_images
     lh, lw = H // 8, W // 8
@@ -198,7 +229,10 @@ def main():
     # a rotating set of distinct inputs larger than the 126 MB L2 (and every step streams GBs of activations)
     in_bytes = n_img * H * W * 3 if "encode" in stages else n_img * lh * lw * 96
     n_sets = max(2, min(8, -(-160_000_000 // in_bytes)))
-    if "encode" in stages:
+    if strong:
+        n_sets = 2
+        inputs = [sharded_patches_gpu(torch, first_img, n_img, H, W, 7919 * i, dev) for i in range(n_sets)]
+    elif "encode" in stages:
         inputs = [synthetic_batch_gpu(torch, n_img, H, W, 1000 * rank + i, dev) for i in range(n_sets)]
     else:
         inputs = [synthetic_latent_gpu(torch, n_img, lh, lw, 1000 * rank + i, dev) for i in range(n_sets)]
@@ -255,33 +289,40 @@ def main():
         t = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
-    mp_per_step = world * n_img * H * W / 1e6
+    mp_per_step = (WORKLOADS[args.workload][0] if strong else world * n_img) * H * W / 1e6
     value = mp_per_step * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API with pinned HOST buffers (H2D + D2H inside the timed region) ----
     def pinned(shape):
         return torch.empty(shape, dtype=torch.uint8, pin_memory=True).numpy()
-    h_in = pinned(tuple(inputs[0].shape)); h_in[...] = inputs[0].cpu().numpy()
-    h_lat = pinned((n_img, lh, lw, 96)); h_rgb = pinned((n_img, H, W, 3))
+    # host staging holds at most 8192 images; a larger per-GPU batch goes through it slice by slice (every slice is copied
+    # in and out, so the byte counts and the timing are those of the whole batch)
+    n_e2e = min(n_img, 8192)
+    slices = -(-n_img // n_e2e)
+    h_in = pinned((n_e2e,) + tuple(inputs[0].shape[1:])); h_in[...] = inputs[0][:n_e2e].cpu().numpy()
+    h_lat = pinned((n_e2e, lh, lw, 96))
+    h_rgb = pinned((n_e2e, H, W, 3)) if "decode" in stages else None
     h2d = d2h = 0
 
     def e2e_step():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        lat = h_in
-        if "encode" in stages and "rate" in stages:
-            lat, r = enc.encode_rate(h_in, out=h_lat); h2d += h_in.nbytes + 6144
-            d2h += h_lat.nbytes + r.hist.nbytes + r.entropy_bits.nbytes + r.bpp.nbytes + 6144
-            hg = torch.from_numpy(r.hist_global.astype(np.int64)).to(dev)
+        hg_host = np.zeros((3, 256), np.uint64)
+        for _s in range(slices):
+            lat = h_in
+            if "encode" in stages and "rate" in stages:
+                lat, r = enc.encode_rate(h_in, out=h_lat, hist_global=hg_host); h2d += h_in.nbytes + 6144
+                d2h += h_lat.nbytes + r.hist.nbytes + r.entropy_bits.nbytes + r.bpp.nbytes + 6144
+            elif "encode" in stages:
+                lat = enc(h_in, out=h_lat); h2d += h_in.nbytes; d2h += h_lat.nbytes
+            elif "rate" in stages:
+                r = nn.rate(enc.handle, lat, H, W, hist_global=hg_host)
+                h2d += lat.nbytes; d2h += r.hist.nbytes + r.entropy_bits.nbytes + r.bpp.nbytes + 6144
+            if "decode" in stages:
+                dec(lat, out=h_rgb); h2d += lat.nbytes; d2h += h_rgb.nbytes
+        if "rate" in stages:
+            hg = torch.from_numpy(hg_host.astype(np.int64)).to(dev)
             nn.dist.allreduce_histogram(hg)
-        elif "encode" in stages:
-            lat = enc(h_in, out=h_lat); h2d += h_in.nbytes; d2h += h_lat.nbytes
-        elif "rate" in stages:
-            r = nn.rate(enc.handle, lat, H, W); h2d += lat.nbytes; d2h += r.hist.nbytes + r.entropy_bits.nbytes + r.bpp.nbytes + 6144
-            hg = torch.from_numpy(r.hist_global.astype(np.int64)).to(dev)
-            nn.dist.allreduce_histogram(hg)
-        if "decode" in stages:
-            dec(lat, out=h_rgb); h2d += lat.nbytes; d2h += h_rgb.nbytes
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -297,47 +338,6 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = mp_per_step * e2e_steps / e2e_s
-
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (event-timed inside the timed region) ----
-    peaks = measured_peaks()
-    px_per_launch = n_img * H * W          # RGB pixels one launch of a kernel covers (micro-batches: see below)
-    dom = max(prof, key=lambda k: prof[k][0]) if prof else None
-    roofline = None
-    kernels = {}
-    for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        launches_per_step = c / args.steps
-        px = px_per_launch / launches_per_step            # pixels per launch
-        avg_ms = t / c
-        entry = {"ms_per_launch": round(avg_ms, 4), "launches_per_step": launches_per_step,
-                 "share_of_step": round(t / ms, 4)}
-        if k in HBM_BOUND and k in BYTES_PER_PX:
-            entry["GB/s"] = round(BYTES_PER_PX[k] * px / avg_ms / 1e6, 1)
-        if k in FLOP_PER_PX and k not in HBM_BOUND:
-            entry["TFLOP/s"] = round(FLOP_PER_PX[k] * px / avg_ms / 1e9, 1)
-        kernels[k] = entry
-    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    traffic = {}
-    if os.path.exists(traffic_path):
-        with open(traffic_path) as f:
-            traffic = json.load(f).get(args.workload, {})
-    if dom:
-        t, c = prof[dom]
-        px = px_per_launch / (c / args.steps)
-        avg_ms = t / c
-        if dom in HBM_BOUND:
-            ach = BYTES_PER_PX[dom] * px / avg_ms / 1e6
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"]}
-        else:
-            ach = FLOP_PER_PX[dom] * px / avg_ms / 1e9
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": round(ach / peaks["tflops"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"],
-                        "note": "algorithmic FLOPs; the fp16 hi/lo split issues 3x as many tensor-core FLOPs"}
 
     # ---- informational: the same steps with the optional fp16 decoder arithmetic (NOT the headline: `value` and `e2e`
     #      above use the decoder that is as exact as the encoder) ----
@@ -381,6 +381,53 @@ def main():
                        "differing_bytes_frac": round(frac, 5), "max_abs_byte_diff": dmax,
                        "note": "Decoder(precision='fp16'): one fp16 product per MAC; within BASELINE's 0.01 dB PSNR, not byte-identical"}
 
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (event-timed inside the timed region) ----
+    peaks = measured_peaks()
+    px_per_launch = n_img * H * W          # RGB pixels one launch of a kernel covers (micro-batches: see below)
+    dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+    roofline = None
+    kernels = {}
+    for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        launches_per_step = c / args.steps
+        px = px_per_launch / launches_per_step            # pixels per launch
+        avg_ms = t / c
+        entry = {"ms_per_launch": round(avg_ms, 4), "launches_per_step": launches_per_step,
+                 "share_of_step": round(t / ms, 4)}
+        if k in HBM_BOUND and k in BYTES_PER_PX:
+            entry["GB/s"] = round(BYTES_PER_PX[k] * px / avg_ms / 1e6, 1)
+        if k in FLOP_PER_PX and k not in HBM_BOUND:
+            entry["TFLOP/s"] = round(FLOP_PER_PX[k] * px / avg_ms / 1e9, 1)
+        kernels[k] = entry
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = {}
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            traffic = json.load(f).get(args.workload, {})
+    if dom:
+        t, c = prof[dom]
+        px = px_per_launch / (c / args.steps)
+        avg_ms = t / c
+        if dom in HBM_BOUND:
+            ach = BYTES_PER_PX[dom] * px / avg_ms / 1e6
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"]}
+        else:
+            ach = FLOP_PER_PX[dom] * px / avg_ms / 1e9
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": round(ach / peaks["tflops"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"],
+                        "note": "algorithmic FLOPs; the fp16 hi/lo split issues 3x as many tensor-core FLOPs"}
+
+    # fingerprint of the all-rank symbol histogram of the last step: for the sharded workload it must not depend on --gpus
+    hist_sha = None
+    if "rate" in stages and "encode" in stages:
+        import hashlib
+        hist_sha = hashlib.sha1(hist_global.cpu().numpy().tobytes()).hexdigest()[:16]
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         sample = max(1, min(n_img, int(round(2.4e6 / (H * W))) or 1))
@@ -390,9 +437,11 @@ def main():
 
     out = {"metric": "encode+decode megapixels/sec", "value": round(value, 2), "unit": "MP/s", "n_gpus": world,
            "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split/f32-accumulate" if args.arith == "tc_split" else "f32",
+           "scaling": "strong" if strong else "weak", "vs_baseline": None,
+           "dtype": "f16x2-split/f32-accumulate" if args.arith == "tc_split" else "f32",
            "data": "synthetic",
            "config": {"workload": f"{args.workload}: {desc}", "images_per_gpu": n_img, "H": H, "W": W, "stages": list(stages),
+                      **({"global_symbol_histogram_sha1": hist_sha} if hist_sha else {}),
                       "weights": "random-init (Keras glorot-uniform)", "arith": args.arith,
                       "l2": f"inputs rotate over {n_sets} distinct batches ({n_sets * in_bytes / 1e6:.0f} MB > 126 MB L2); "
                             "each step streams > 1 GB of activations"},
