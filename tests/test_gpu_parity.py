@@ -470,3 +470,29 @@ def test_load_reads_tensorflow_checkpoints(nn, codec_factory, tmp_path):
     sym = enc(img)
     assert np.array_equal(sym, enc_ref(img))
     assert np.array_equal(dec(sym), dec_ref(sym))
+
+
+def test_random_shapes_against_oracle(nn, codec_factory):
+    """Seeded random batch / image sizes (multiples of 8 up to 296 x 344: partial tiles on both edges, 1-7 images)
+    against the fp64 oracle: every mismatching symbol must be a rounding tie (+-1, inside the tie band), and over all
+    shapes together the mismatch fraction must meet the 1e-4 criterion (single small images get Poisson slack).  The
+    fused histogram must equal the histogram of the symbols; the decoder is compared with the FFMA arithmetic."""
+    eY, eC, dY, dC = make_weights("spread")
+    enc_tc, dec_tc = codec_factory("spread", "tc_split")
+    _e, dec_ff = codec_factory("spread", "simt_f32")
+    rng = np.random.default_rng(77)
+    bad = total = 0
+    for _ in range(14):
+        n, h, w = int(rng.integers(1, 8)), 8 * int(rng.integers(1, 38)), 8 * int(rng.integers(1, 44))
+        img = synthetic_images(n, h, w, seed=int(rng.integers(0, 1 << 30)))
+        sym, r = enc_tc.encode_rate(img)
+        pre64 = O.encode_prequant(img, eY, eC, "f64")
+        sym64 = O.quantise(pre64)
+        tie = np.abs(pre64 * 255.0 - np.floor(pre64 * 255.0) - 0.5)
+        lam = SYMBOL_MISMATCH_LIMIT * sym.size
+        bad += check_symbols(sym, sym64, tie, min_allow=int(lam + 4 * np.sqrt(lam) + 2))
+        total += sym.size
+        assert np.array_equal(r.hist.astype(np.int64), O.histogram(sym)), (n, h, w)
+        rec, rec_ff = dec_tc(sym64), dec_ff(sym64)
+        assert np.abs(rec.astype(int) - rec_ff.astype(int)).max() <= 1 and (rec != rec_ff).mean() < 3e-4, (n, h, w)
+    assert bad <= SYMBOL_MISMATCH_LIMIT * total, f"{bad} of {total} symbols differ from the fp64 oracle"
