@@ -51,15 +51,10 @@ struct TcStep {
   int16_t koff;        // element offset inside the view's innermost dimension
   int16_t w_row;       // first row of this step's [COUT x KSLAB] tile in the weight matrix
   int8_t ks_begin, ks_end;  // 16-element k-steps of the slab that carry non-zero weights
-  int8_t chain_end;    // 1 = the accumulation chain (one TMEM slot) ends after this step
-  int8_t pad_;
+  int16_t pad_;
 };
-struct TcJob {
+struct TcJob {             // host-side description; nnic_api.cu lowers it to the kernel's TcPatchJob
   int nsteps;
-  int nchains;         // number of accumulation chains (TMEM slots) per tile
-  uint32_t chain_end_mask;   // bit s = steps[s].chain_end
-  uint32_t half_mask;        // bit s = step s only uses the upper half of its slab (ks_begin = ks_end/2)
-  int ks_end;                // k-steps per full slab (4 for 128-byte rows, 2 for 64-byte rows)
   int out_oy, out_ox;  // output offset of this phase
   TcStep steps[MAX_STEPS];
 };

@@ -68,16 +68,16 @@ cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float
 // ---- tensor-core convolutions ------------------------------------------------------------------------
 enum TcOutMode { TC_OUT_SPLIT = 0, TC_OUT_F32 = 1, TC_OUT_QUANT = 2 };
 
-// ---- tensor-core convolution, halo-patch variant (tc_conv_patch.cu): 64 or 32 -> 64 channels, taps within the
-//      3x3 neighbourhood (conv3/4, dconv5/6, the four phases of dconv7 and dconv1) ------------------------------------
+// ---- tensor-core convolution on a halo patch (tc_conv_patch.cu): every GEMM-shaped layer; all taps lie within the
+//      3x3 neighbourhood of the tile in the view the layer reads ---------------------------------------------------
 struct TcPatchStep {
   uint32_t a_off;      // byte offset of the tap's first pixel row inside the hi patch (tc_patch_a_offset)
-  int16_t w_row;       // first row of this tap's [64 x 64] tile in the weight matrix
+  int16_t w_row;       // first row of this tap's [COUT x K] tile in the weight matrix
   int16_t pad_;
 };
 struct TcPatchJob {
-  int nsteps, nchains;
-  uint32_t chain_end_mask;
+  int nsteps;
+  int nchains;         // accumulation chains (TMEM slots) per tile: three taps each, never across patches
   int out_oy, out_ox;
   TcPatchStep steps[MAX_STEPS];
 };

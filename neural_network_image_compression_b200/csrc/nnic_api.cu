@@ -264,27 +264,6 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
     }
     L.rows_per_set = 25 * sp.cout;
   }
-  // Accumulation chains: the tensor core truncates its fp32 accumulator on every MMA, so long chains
-  // drift (measured: ~50 ulp over 108 MMAs).  Each chain of <= ~12 k-steps gets its own TMEM slot and the
-  // epilogue adds the chains with round-to-nearest fp32 adds.
-  for (int ji = 0; ji < L.njobs; ++ji) {
-    TcJob& j = L.jobs[ji];
-    int total_ks = 0;
-    for (int s = 0; s < j.nsteps; ++s) total_ks += j.steps[s].ks_end - j.steps[s].ks_begin;
-    int nchains = (total_ks + 11) / 12;
-    if (nchains < 1) nchains = 1;
-    if (nchains > j.nsteps) nchains = j.nsteps;
-    j.nchains = nchains;
-    for (int c = 0; c < nchains; ++c) {
-      const int last = ((c + 1) * j.nsteps) / nchains - 1;   // steps split as evenly as possible
-      j.steps[last].chain_end = 1;
-    }
-    j.chain_end_mask = 0; j.half_mask = 0; j.ks_end = L.row_bytes / 32;
-    for (int s = 0; s < j.nsteps; ++s) {
-      if (j.steps[s].chain_end) j.chain_end_mask |= 1u << s;
-      if (j.steps[s].ks_begin != 0) j.half_mask |= 1u << s;
-    }
-  }
 }
 
 // value of the TC weight matrix of `sp` at (row, col) for Keras kernel `kern`
@@ -555,7 +534,6 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       const TcJob& src = L.jobs[j];
       TcPatchJob& dst = pp.jobs[j];
       dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + 2) / 3;   // the patch kernel chains three taps per TMEM slot
-      dst.chain_end_mask = 0;
       dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
       for (int s = 0; s < src.nsteps; ++s) {
         dst.steps[s].a_off = tc_patch_a_offset(src.steps[s].dy, src.steps[s].dx, L.row_bytes);
