@@ -93,6 +93,7 @@ struct TcPatchParams {
   int seg_steps[4];
   int cout;                   // 64, or 32 (conv8)
   int fast;                   // one fp16 product per MAC, hi planes only (decoder, nnic_set_decode_precision)
+  int cluster;                // 2: CTA pairs share every weight tile through TMA multicast; else 1
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;

@@ -97,6 +97,31 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- thread-block clusters: weight tiles are multicast to the CTAs of a cluster ------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the tile lands at the same shared-memory offset in every CTA of `cta_mask`, and each of them gets the byte count
+// on its own mbarrier at the offset of `bar`
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrives on the mbarrier at the offset of `bar` in every CTA of `cta_mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // one lane of the (fully converged) warp; the same lane every time, so MMAs and their commits share a thread
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

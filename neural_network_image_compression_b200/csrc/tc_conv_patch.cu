@@ -75,7 +75,10 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
 
 // FAST: one fp16 product per MAC (A_hi x W_hi only, activations written as one fp16 plane) -- the decoder's optional
 // reduced-precision arithmetic (nnic_set_decode_precision); the lo planes are neither read nor written.
-template <int RB, int NSPLIT, int COUT, bool FAST>
+// CL = thread-block cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring items in lockstep
+// and every weight tile is fetched from L2 once and MULTICAST into both shared memories (the CTAs alternate as the
+// issuer); a ring slot is refilled when the MMAs of both CTAs have released it.
+template <int RB, int NSPLIT, int COUT, bool FAST, int CL>
 __global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -106,7 +109,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kNumMma); }
-    for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -121,8 +124,14 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync();                  // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = tiles_x * tiles_y;
+  // cluster rounds: the CTAs of a cluster take items base + rank; a CTA without an item in the last round still mirrors
+  // the weight protocol (arms its barriers, releases the slots) so that its peer is never left waiting
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int base0 = (int)blockIdx.x - crank;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1u);
 
   if (warp == kPatchWarp) {
     // ===================== TMA producer: activation patches =====================
@@ -150,9 +159,15 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== TMA producer: weight groups =====================
     int ws = 0; uint32_t wphase = 0;
     long long tw_patch = 0, tw_w = 0, t_begin = TICK();
-    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-      const int p = it / tiles_per_plane;
-      const int set = p < prm.n_split ? 0 : 1;
+    for (int base = base0; base < num_items; base += gridDim.x) {
+      const int it = base + crank, it_peer = base + (crank ^ 1);
+      const bool active = it < num_items, peer_active = CL > 1 && it_peer < num_items;
+      const int set_my = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
+      const int set_peer = (it_peer / tiles_per_plane) < prm.n_split ? 0 : 1;
+      const int set = active ? set_my : set_peer;
+      // tiles are shared unless both CTAs are active on different weight sets (Y / CbCr boundary inside the pair)
+      const bool shared = CL > 1 && (!(active && peer_active) || set_my == set_peer);
+      int tap = 0;
       const int nseg = prm.npatch;
       for (int seg = 0; seg < nseg; ++seg) {
       const int njobs_seg = nseg == 1 ? prm.njobs : 1;
@@ -160,7 +175,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int sbeg = 0;
         for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
         const int send = nseg == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
-        for (int s0 = sbeg; s0 < send; ++s0) {                 // one weight tile per tap, in the order the issuers consume them
+        for (int s0 = sbeg; s0 < send; ++s0, ++tap) {          // one weight tile per tap, in the order the issuers consume them
           { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
             uint8_t* wb = w_base + ws * W_SLOT;
@@ -169,8 +184,14 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             } else {
               mbar_expect_tx(&w_full[ws], FAST ? W_TILE : W_SLOT);
               const int wrow = set * prm.rows_per_set + prm.jobs[j].steps[s0].w_row;
-              tma_load_2d(&map_w_hi, wb, &w_full[ws], 0, wrow);
-              if (!FAST) tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
+              if (CL == 1) {
+                tma_load_2d(&map_w_hi, wb, &w_full[ws], 0, wrow);
+                if (!FAST) tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow);
+              } else if (!shared || (tap & (CL - 1)) == crank) {
+                const uint16_t mask = shared ? kAllCtas : (uint16_t)(1u << crank);
+                tma_load_2d_multicast(&map_w_hi, wb, &w_full[ws], 0, wrow, mask);
+                if (!FAST) tma_load_2d_multicast(&map_w_lo, wb + W_TILE, &w_full[ws], 0, wrow, mask);
+              }
             }
           }
           __syncwarp();
@@ -191,9 +212,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int pb = 0; uint32_t pphase = 0;
     int ws = 0; uint32_t wphase = 0;
     int slot = 0; uint32_t slot_phase = 0;
-    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    for (int base = base0; base < num_items; base += gridDim.x) {
+      const bool active = base + crank < num_items;
       for (int seg = 0; seg < prm.npatch; ++seg) {
-      { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, error_flag, 3); tw_patch += TICK() - t0; }
+      if (active) { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, error_flag, 3); tw_patch += TICK() - t0; }
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
       const int njobs_seg = prm.npatch == 1 ? prm.njobs : 1;
       for (int j = 0; j < njobs_seg; ++j) {
@@ -210,7 +232,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           uint32_t a_off[GTAPS];
 #pragma unroll
           for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
-          { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); tw_slot += TICK() - t0; }
+          if (active) { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); tw_slot += TICK() - t0; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
           const long long ti0 = TICK();
@@ -222,7 +244,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               if (k < ntaps) {
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, error_flag, 5); tw_w += TICK() - t1; }
                 tc_fence_after();
-                if (!(prm.dbg & 1)) {
+                if (active && !(prm.dbg & 1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
                   const uint64_t w_hl = make_desc_sbo(w_u32 + w * W_SLOT, C::W_SBO, C::LAYOUT);   // W_hi followed by W_lo
@@ -240,11 +262,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                   }
                 }
-                umma_commit(&w_empty[w]);
+                if (CL > 1) umma_commit_multicast(&w_empty[w], kAllCtas); else umma_commit(&w_empty[w]);
                 if (++w == WSLOTS) { w = 0; wp ^= 1; }
               }
             }
-            umma_commit(&slot_full[slot]);
+            if (active) umma_commit(&slot_full[slot]);
           }
           __syncwarp();
           ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
@@ -252,9 +274,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
         }
       }
-      if (elect_one()) umma_commit(&patch_empty[pb]);      // every MMA of this segment has read the patch
-      __syncwarp();
-      if (++pb == NSETS) { pb = 0; pphase ^= 1; }
+      if (active) {
+        if (elect_one()) umma_commit(&patch_empty[pb]);      // every MMA of this segment has read the patch
+        __syncwarp();
+        if (++pb == NSETS) { pb = 0; pphase ^= 1; }
+      }
       }
     }
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
@@ -410,6 +434,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();                  // no CTA leaves while its peer may still multicast to it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -420,22 +445,45 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT, int COUT, bool FAST = false>
+template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_patch<RB, NSPLIT, COUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES);
+  using Cfg = PCfg<RB, NSPLIT, COUT>;
+  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL>;
+  static int max_grid = 0;                     // CTAs that can be co-resident (persistent kernel: one wave)
+  if (!max_grid) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    max_grid = num_sms;
+    if (CL > 1) {
+      cudaLaunchConfig_t probe = {};
+      probe.gridDim = dim3((num_sms / CL) * CL); probe.blockDim = dim3(Cfg::kThreads); probe.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute pa[1];
+      pa[0].id = cudaLaunchAttributeClusterDimension; pa[0].val.clusterDim.x = CL; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+      probe.attrs = pa; probe.numAttrs = 1;
+      int nclusters = 0;
+      e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &probe);
+      if (e != cudaSuccess) return e;
+      if (nclusters < 1) return cudaErrorInvalidConfiguration;
+      max_grid = nclusters * CL < num_sms ? nclusters * CL : (num_sms / CL) * CL;
+    }
   }
   const int tiles_x = (prm.Wp + kTileCols - 1) / kTileCols, tiles_y = (prm.Hp + kTileRows - 1) / kTileRows;
   const long long items = (long long)tiles_x * tiles_y * prm.P;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_conv_patch<RB, NSPLIT, COUT, FAST><<<grid, PCfg<RB, NSPLIT, COUT>::kThreads, PCfg<RB, NSPLIT, COUT>::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
-  return cudaGetLastError();
+  long long want = (items + CL - 1) / CL * CL;               // whole clusters
+  const int grid = want < max_grid ? (int)want : max_grid;
+  if (CL == 1) {
+    kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
 }
 
 cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
@@ -448,6 +496,13 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
     if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 128) return launch_patch_impl<128, 2, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 64) return launch_patch_impl<64, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (prm.cluster == 2) {                      // weight tiles multicast to CTA pairs
+    if (row_bytes == 128 && prm.cout == 32) return launch_patch_impl<128, 2, 32, false, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64, false, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    if (row_bytes == 128) return launch_patch_impl<128, 2, 64, false, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    if (row_bytes == 64) return launch_patch_impl<64, 4, 64, false, 2>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     return cudaErrorInvalidValue;
   }
   if (row_bytes == 128 && prm.cout == 32) return launch_patch_impl<128, 2, 32>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);

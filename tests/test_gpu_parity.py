@@ -496,3 +496,24 @@ def test_random_shapes_against_oracle(nn, codec_factory):
         rec, rec_ff = dec_tc(sym64), dec_ff(sym64)
         assert np.abs(rec.astype(int) - rec_ff.astype(int)).max() <= 1 and (rec != rec_ff).mean() < 3e-4, (n, h, w)
     assert bad <= SYMBOL_MISMATCH_LIMIT * total, f"{bad} of {total} symbols differ from the fp64 oracle"
+
+
+def test_cluster_multicast_variant_is_bit_identical(nn, monkeypatch):
+    """NNIC_TC_CLUSTER=1 (CTA pairs sharing every weight tile through TMA multicast, opt-in: measured no faster,
+    profiles/r1_cluster_multicast_ab.log) must give the same bytes as the default kernels, including an odd number of
+    work items (the last cluster runs with one idle CTA) and a pair that straddles the Y / CbCr weight sets."""
+    eY, eC, dY, dC = make_weights("spread")
+
+    def codec():
+        e, d = nn.Encoder(0), nn.Decoder(0)
+        e.set_weights(0, eY); e.set_weights(1, eC); d.set_weights(0, dY); d.set_weights(1, dC)
+        return e, d
+    enc0, dec0 = codec()
+    monkeypatch.setenv("NNIC_TC_CLUSTER", "1")
+    enc1, dec1 = codec()
+    for shape in ((1, 8, 8), (1, 72, 40), (3, 136, 264), (5, 64, 96)):
+        img = synthetic_images(*shape, seed=71)
+        sym0, r0 = enc0.encode_rate(img)
+        sym1, r1 = enc1.encode_rate(img)
+        assert np.array_equal(sym0, sym1) and np.array_equal(r0.hist, r1.hist), shape
+        assert np.array_equal(dec0(sym0), dec1(sym0)), shape
