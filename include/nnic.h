@@ -31,7 +31,7 @@ typedef struct nnic_handle nnic_t;
 enum nnic_status {
   NNIC_OK = 0,
   NNIC_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, bad enum */
-  NNIC_ERR_SHAPE = -2,         /* shape not supported by the requested arithmetic mode */
+  NNIC_ERR_SHAPE = -2,         /* reserved: sizes the tensor-core kernels cannot take are routed to the FFMA kernels */
   NNIC_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see nnic_last_error */
   NNIC_ERR_NO_WEIGHTS = -4,    /* a network needed by the call has unset layers */
   NNIC_ERR_NO_DEVICE = -5      /* no usable sm_100 device */
