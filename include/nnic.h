@@ -9,6 +9,8 @@
  * nnic_status, and nnic_last_error() gives the text for the most recent failure on a handle.
  *
  * Threading: a handle is bound to one CUDA device and is not thread-safe.  One handle per GPU.
+ * Calls on one handle share its scratch memory and weights: with NNIC_MEM_DEVICE they must be stream-ordered
+ * (same stream, or the caller synchronises between streams).
  * Memory kinds: NNIC_MEM_HOST pointers are ordinary host memory (pageable or pinned); the call
  * copies in/out and returns after the result is in the caller's buffer.  NNIC_MEM_DEVICE pointers
  * are device memory on the handle's device; the call only enqueues work on `stream` and returns.
