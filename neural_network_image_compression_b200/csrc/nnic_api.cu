@@ -73,7 +73,7 @@ struct nnic_handle {
   int micro_batch = 0;
   bool decode_fp16 = false;         // nnic_set_decode_precision: decoder GEMM layers with one fp16 product per MAC
   uint32_t* fused_hist = nullptr;   // set around conv8's launch by encode_batch: device [nb][3][256] counts to add to
-  bool tc_cluster = false;          // weight tiles multicast to CTA pairs (NNIC_TC_CLUSTER=1)
+  int tc_cluster = 0;               // weight tiles multicast to CTA pairs: NNIC_TC_CLUSTER=0 never, 1 residual layers, 2 all
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   EncodeTiledFn encode_tiled = nullptr;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
@@ -549,7 +549,8 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.out_mode = out_mode;
     pp.cout = L.cout;
     pp.fast = (net == 1 && h->decode_fp16) ? 1 : 0;
-    pp.cluster = (!pp.fast && h->tc_cluster) ? 2 : 1;
+    // tc_cluster: 0 never (default: no measurable gain, profiles/r1_cluster_multicast_ab.log), 1 residual layers only, 2 every layer
+    pp.cluster = (!pp.fast && (h->tc_cluster == 2 || (h->tc_cluster == 1 && res))) ? 2 : 1;
     pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
     pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
     pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
@@ -754,7 +755,7 @@ int nnic_create(int device, nnic_t** out) {
   h->encode_tiled = (EncodeTiledFn)fn;
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
-  if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env);
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
