@@ -231,3 +231,21 @@ def test_tensorflow_checkpoint_reader(nn, tmp_path):
         open(str(tmp_path / "bad.index"), "wb").write(b"\\x00" * 64)
         tfbundle.read_index(str(tmp_path / "bad.index"))
     assert tfbundle.mask_crc(tfbundle.crc32c(b"123456789")) == (((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` needs no GPU: exactly one JSON line on stdout with the contract's keys."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c3",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "MP/s" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
