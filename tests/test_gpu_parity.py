@@ -517,3 +517,29 @@ def test_cluster_multicast_variant_is_bit_identical(nn, monkeypatch):
         sym1, r1 = enc1.encode_rate(img)
         assert np.array_equal(sym0, sym1) and np.array_equal(r0.hist, r1.hist), shape
         assert np.array_equal(dec0(sym0), dec1(sym0)), shape
+
+
+def test_bench_line_has_the_contract_keys():
+    """`python bench.py` on one GPU: one JSON line with value, e2e (host copies counted), roofline, cpu_baseline, clocks and a
+    positive launch count; the roofline kernel's share comes from the per-launch event timing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "5", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "encode+decode megapixels/sec" and d["unit"] == "MP/s" and d["n_gpus"] == 1 and d["value"] > 100
+    assert d["steps"] == 5 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["e2e"]["value"] > 100 and d["e2e"]["h2d_bytes_per_step"] >= 24 * 512 * 768 * 3
+    assert d["e2e"]["d2h_bytes_per_step"] >= 24 * 512 * 768 * 3 + 24 * 64 * 96 * 96
+    assert d["gpu_launches"] >= 5 * 10
+    rf = d["roofline"]
+    assert rf["bound"] in ("hbm", "tensor") and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+    assert rf["kernel"] in d["kernels"] and rf["traffic"] is not None
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "model" not in d["config"]
