@@ -10,8 +10,10 @@ TensorFlow (not installed here, un-vendored, version pinned only by the director
 names tf1_13/ and tf2_0/).  This file restates the published TensorFlow/Keras
 semantics (SAME padding, Conv2D HWIO kernels, Conv2DTranspose HWOI kernels,
 leaky_relu alpha=0.2, round-half-to-even) and anchors on the reference call sites
-cited below.  The conv arithmetic is checked against an independent naive-loop
-restatement in oracle/naive.py.
+cited below.  It is pinned, as far as that is possible without TensorFlow, by two
+implementations that share no code with it: the naive-loop NumPy convolutions of
+oracle/naive.py and the plain-C restatement of the WHOLE path in oracle/nnic_oracle.c
+(fp64; agrees to 5e-15 on even, odd and minimal sizes, tests/test_oracle.py).
 
 Reference call sites restated here (paths relative to /root/reference):
   tf2_0/src/utils.py:7-9      colour constants (ycbcr_kernel, inverse via linalg.inv, offsets)

@@ -115,3 +115,28 @@ def test_golden_vectors(name, wname):
     hist, ent, bpp, _ = O.rate(g[f"{wname}_sym64"], img.shape[1], img.shape[2], "f32")
     assert np.array_equal(hist, g[f"{wname}_hist"].astype(np.int64))
     assert np.allclose(bpp, g[f"{wname}_bpp"], rtol=1e-5)
+
+
+# ---- second, independent restatement in plain C (oracle/nnic_oracle.c) ---------------------------------------------
+def test_c_restatement_agrees_with_the_python_oracle():
+    """oracle/nnic_oracle.c (explicit loops, written from the reference call sites, shares no code with the torch-based
+    oracle) must give the same fp64 pre-quantisation values to rounding noise, for even, odd and minimal sizes, both
+    weight sets, encoder and decoder; hence identical symbols / bytes except exactly at ties."""
+    from conftest import make_weights, synthetic_images, load_golden
+    from oracle import c_oracle as CO
+    for wname in ("default", "spread"):
+        eY, eC, dY, dC = make_weights(wname)
+        cases = [synthetic_images(2, 40, 56, seed=5), synthetic_images(1, 37, 29, seed=6), synthetic_images(1, 8, 8, seed=7),
+                 load_golden("kodim21_crop")["input"][:, :64, :96]]
+        for img in cases:
+            a = CO.encode_prequant(img, eY, eC)
+            b = O.encode_prequant(img, eY, eC, "f64")
+            assert a.shape == b.shape and np.abs(a - b).max() < 1e-12
+            sym = O.quantise(b)
+            tie = np.abs(b * 255.0 - np.floor(b * 255.0) - 0.5)
+            diff = CO.quantise(a) != sym
+            assert np.all(tie[diff] < 1e-9)
+            assert np.array_equal(CO.quantise(b), sym)                   # round-half-to-even in C == np.round
+            ra = CO.decode_prequant(sym, dY, dC)
+            rb = O.decode_prequant(sym, dY, dC, "f64")
+            assert ra.shape == rb.shape and np.abs(ra - rb).max() < 1e-12
