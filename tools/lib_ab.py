@@ -7,4 +7,4 @@ for rep in range(rounds):
         out = subprocess.run([sys.executable, "bench.py", "--steps", "60", "--no-cpu-baseline"], capture_output=True, text=True, env=env).stdout
         d = json.loads(out)
         k = d["kernels"]
-        print(os.path.basename(lib).ljust(18), "step %.4f ms |" % d["ms_per_step"], " ".join("%s %.4f" % (n, k[n]["ms_per_launch"]) for n in ("conv2", "conv3", "conv4", "conv8", "dconv1", "dconv5", "dconv6", "dconv7")), flush=True)
+        print(os.path.basename(lib).ljust(18), "step %.4f ms |" % d["ms_per_step"], " ".join("%s %.4f" % (n, k[n]["ms_per_launch"]) for n in ("conv1", "dconv8", "conv2", "conv3", "conv4", "conv8", "dconv1", "dconv5", "dconv6", "dconv7")), flush=True)
