@@ -33,7 +33,7 @@ typedef struct nnic_handle nnic_t;
 enum nnic_status {
   NNIC_OK = 0,
   NNIC_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, bad enum */
-  NNIC_ERR_SHAPE = -2,         /* reserved: sizes the tensor-core kernels cannot take are routed to the FFMA kernels */
+  NNIC_ERR_SHAPE = -2,         /* shape not supported by a development toggle (never returned by a default handle) */
   NNIC_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see nnic_last_error */
   NNIC_ERR_NO_WEIGHTS = -4,    /* a network needed by the call has unset layers */
   NNIC_ERR_NO_DEVICE = -5      /* no usable sm_100 device */
@@ -51,9 +51,8 @@ enum { NNIC_LAYERS_PER_NET = 5 };
 
 /* Arithmetic of the eight GEMM-shaped layers (conv2/3/4/8, dconv1/5/6/7):
  *   NNIC_ARITH_TC_SPLIT  tcgen05 tensor cores, fp16 hi+lo split operands (3 MMAs per product),
- *                        fp32 accumulation in TMEM.  Default.  Image sizes that are not multiples of 8 (the
- *                        parity views of the stride-2 layers need even sizes at every stage) are encoded by the
- *                        NNIC_ARITH_SIMT_F32 kernels for that call -- on the GPU, within the same tolerance.
+ *                        fp32 accumulation in TMEM.  Default.  Any image size >= 1x1 (odd sizes at any stage are
+ *                        stored with an even, zero-filled pitch so that the stride-2 parity views stay valid).
  *   NNIC_ARITH_SIMT_F32  plain fp32 FFMA kernels (any H, W >= 1).  Cross-check path.
  * conv1, dconv8, colour, quantise, histogram and pack kernels are fp32/integer in both modes. */
 enum nnic_arith { NNIC_ARITH_TC_SPLIT = 0, NNIC_ARITH_SIMT_F32 = 1 };

@@ -97,6 +97,7 @@ struct TcPatchParams {
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;
+  int Hs, Ws;                 // storage rows / columns per plane of the output and the residual (>= Ho, Wo)
   int rows_per_set;
   float inv_scale[2];
   const float* bias;
@@ -124,6 +125,7 @@ struct TcConv1Params {
   const uint8_t* rgb;         // u8 [N,H,W,3] (colour transform fused), or
   const float* planes;        // f32 [3N,H,W,1]
   int N, H, W, Ho, Wo, pad_t, pad_l;
+  int Hs, Ws;                 // storage rows / columns per plane of the output (>= Ho, Wo)
   const __half* w_hi;         // device [2 sets][32 channels][32 taps (25 used)] fp16, scaled
   const __half* w_lo;
   const float* bias;          // device [2][32]

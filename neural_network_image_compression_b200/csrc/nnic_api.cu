@@ -190,18 +190,20 @@ int make_map(nnic_t* h, CUtensorMap* map, void* base, int rank, const cuuint64_t
   if (r != CUDA_SUCCESS) return fail(h, NNIC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
-// activation view [inner, X, PY, Y, P] of a split-fp16 tensor [P,H,W,C]
+// activation view [inner, X, PY, Y, P] of a split-fp16 tensor [P,H,W,C] stored with Hs x Ws pixels per plane.
+// Plain view: logical extents, so everything beyond H x W is zero-filled by the TMA unit.  Parity view: the (even)
+// storage extents; a padding row / column is real memory there and must hold zeros.
 int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, int W, int C, bool parity, int kslab,
-                 int row_bytes, int box_cols = 8, int box_rows = 16) {
+                 int row_bytes, int box_cols, int box_rows, int Hs, int Ws) {
   cuuint64_t dims[5], strides[4];
   if (!parity) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = P;
-    strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)W * C * 2;
-    strides[3] = (cuuint64_t)H * W * C * 2;
+    strides[0] = (cuuint64_t)C * 2; strides[1] = (cuuint64_t)Ws * C * 2; strides[2] = (cuuint64_t)Ws * C * 2;
+    strides[3] = (cuuint64_t)Hs * Ws * C * 2;
   } else {
-    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = P;
-    strides[0] = (cuuint64_t)2 * C * 2; strides[1] = (cuuint64_t)W * C * 2; strides[2] = (cuuint64_t)2 * W * C * 2;
-    strides[3] = (cuuint64_t)H * W * C * 2;
+    dims[0] = 2 * C; dims[1] = Ws / 2; dims[2] = 2; dims[3] = Hs / 2; dims[4] = P;
+    strides[0] = (cuuint64_t)2 * C * 2; strides[1] = (cuuint64_t)Ws * C * 2; strides[2] = (cuuint64_t)2 * Ws * C * 2;
+    strides[3] = (cuuint64_t)Hs * Ws * C * 2;
   }
   cuuint32_t box[5] = {(cuuint32_t)kslab, (cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};
   return make_map(h, map, const_cast<__half*>(base), 5, dims, strides, box, row_bytes);
@@ -212,6 +214,30 @@ int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, 
 inline float kval(const LayerSpec& sp, const std::vector<float>& kern, int a, int b, int ci, int co) {
   if (!sp.transposed) return kern[(((size_t)a * sp.k + b) * sp.cin + ci) * sp.cout + co];   // [kh,kw,Cin,Cout]
   return kern[(((size_t)a * sp.k + b) * sp.cout + co) * sp.cin + ci];                        // [kh,kw,Cout,Cin]
+}
+
+// Stride-2 convolution (conv2, conv8) read through the parity view: input row of output row Y and kernel row a is
+// 2Y - pb + a with pb = TF's SAME pad-before of that axis (1 for an even input size, 2 for an odd one), i.e. view row
+// Y + ((a - pb) >> 1) of row parity (a - pb) & 1; columns likewise.  conv2 (Cin 32) pairs the two column parities of a
+// view column in one 64-wide K slab: tile (a, jj) holds kernel columns 2jj + pb + {0, 1}.
+void build_s2_program(const LayerSpec& sp, int pby, int pbx, TcJob& j) {
+  memset(&j, 0, sizeof j);
+  if (sp.cin == 32) {
+    j.nsteps = 15;
+    for (int a = 0; a < 5; ++a) for (int jj = -1; jj <= 1; ++jj) {
+      TcStep& s = j.steps[a * 3 + jj + 1];
+      s.dy = (a - pby) >> 1; s.py = (a - pby) & 1; s.dx = jj; s.koff = 0;
+      s.w_row = ((pbx == 2 ? 15 : 0) + a * 3 + jj + 1) * sp.cout;
+      s.ks_begin = (pbx == 1 && jj == -1) ? 2 : 0; s.ks_end = 4;      // pad-before 1: tile jj = -1 only has the odd column
+    }
+  } else {
+    j.nsteps = 25;
+    for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) {
+      TcStep& s = j.steps[a * 5 + b];
+      s.dy = (a - pby) >> 1; s.py = (a - pby) & 1; s.dx = (b - pbx) >> 1; s.koff = ((b - pbx) & 1) * 64;
+      s.w_row = (a * 5 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
+    }
+  }
 }
 
 void build_tc_program(const LayerSpec& sp, TcLayer& L) {
@@ -227,24 +253,11 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
       s.dy = a - 1; s.dx = b - 1; s.py = 0; s.koff = 0; s.w_row = (a * 3 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
     }
     L.rows_per_set = 9 * sp.cout;
-  } else if (!sp.transposed && sp.s == 2 && sp.cin == 32) {   // conv2: column taps paired in one 64-wide slab
+  } else if (!sp.transposed && sp.s == 2) {     // conv2, conv8: even input sizes (pad-before 1); other sizes per call
     L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
-    TcJob& j = L.jobs[0]; j.nsteps = 15;
-    for (int a = 0; a < 5; ++a) for (int jj = -1; jj <= 1; ++jj) {
-      TcStep& s = j.steps[a * 3 + jj + 1];
-      s.dy = (a - 1) >> 1; s.py = (a - 1) & 1; s.dx = jj; s.koff = 0; s.w_row = (a * 3 + jj + 1) * sp.cout;
-      s.ks_begin = jj == -1 ? 2 : 0; s.ks_end = 4;
-    }
-    L.rows_per_set = 15 * sp.cout;
-  } else if (!sp.transposed && sp.s == 2) {     // conv8
-    L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
-    TcJob& j = L.jobs[0]; j.nsteps = 25;
-    for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) {
-      TcStep& s = j.steps[a * 5 + b];
-      s.dy = (a - 1) >> 1; s.py = (a - 1) & 1; s.dx = (b - 1) >> 1; s.koff = ((b - 1) & 1) * 64;
-      s.w_row = (a * 5 + b) * sp.cout; s.ks_begin = 0; s.ks_end = 4;
-    }
-    L.rows_per_set = 25 * sp.cout;
+    build_s2_program(sp, 1, 1, L.jobs[0]);
+    // conv2 keeps two tile sets: rows [0, 15*64) pair the column taps for pad-before 1, rows [15*64, 30*64) for pad-before 2
+    L.rows_per_set = sp.cin == 32 ? 30 * sp.cout : 25 * sp.cout;
   } else if (sp.transposed && sp.s == 1) {      // dconv5, dconv6: out[o] = sum_a x[o+1-a] K[a]
     L.row_bytes = 128; L.kslab = 64; L.njobs = 1;
     TcJob& j = L.jobs[0]; j.nsteps = 9;
@@ -271,8 +284,9 @@ void build_tc_program(const LayerSpec& sp, TcLayer& L) {
 float tc_weight_at(const LayerSpec& sp, const std::vector<float>& kern, int row, int col) {
   const int tile = row / sp.cout, co = row % sp.cout;
   if (!sp.transposed && sp.s == 2 && sp.cin == 32) {       // conv2 paired slabs
-    const int a = tile / 3, jj = tile % 3 - 1, px = col / 32, ci = col % 32;
-    const int b = 2 * jj + 1 + px;
+    const int pbx = tile >= 15 ? 2 : 1, t = tile % 15;
+    const int a = t / 3, jj = t % 3 - 1, px = col / 32, ci = col % 32;
+    const int b = 2 * jj + pbx + px;
     if (b < 0 || b > 4) return 0.0f;
     return kval(sp, kern, a, b, ci, co);
   }
@@ -459,11 +473,16 @@ void build_simt_jobs(const LayerSpec& sp, int Hi, int Wi, SimtJobs& J) {
 struct Act {          // an activation tensor [P,H,W,C] in one of the two storage forms
   __half* hi = nullptr; __half* lo = nullptr; float* f32 = nullptr;
   int H = 0, W = 0, C = 0;
+  int Hs = 0, Ws = 0;   // storage rows / columns per plane (>= H, W): even for the tensors the stride-2 parity views read
 };
+inline int even_up(int v) { return v + (v & 1); }
 
-Act take_act(nnic_t* h, bool split, int P, int H, int W, int C) {
+// even_storage: rows and columns are padded to even counts (the parity views [2C, W/2, 2, H/2, P] need them); the caller
+// zeroes the tensor when padding was added, so that the extra row / column reads as TF's SAME zero padding
+Act take_act(nnic_t* h, bool split, int P, int H, int W, int C, bool even_storage = false) {
   Act a; a.H = H; a.W = W; a.C = C;
-  const size_t n = (size_t)P * H * W * C;
+  a.Hs = even_storage ? even_up(H) : H; a.Ws = even_storage ? even_up(W) : W;
+  const size_t n = (size_t)P * a.Hs * a.Ws * C;
   if (split) { a.hi = (__half*)arena_take(h, n * 2); a.lo = (__half*)arena_take(h, n * 2); }
   else a.f32 = (float*)arena_take(h, n * 4);
   return a;
@@ -501,8 +520,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
   TcLayer& L = h->tc[net][gi];
   {
     CUtensorMap pa_hi, pa_lo;
-    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
-    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18)) return rc;
+    if (L.parity_view && ((in.Hs | in.Ws) & 1)) return fail(h, NNIC_ERR_CUDA, "internal: stride-2 input without even storage");
+    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18, in.Hs, in.Ws)) return rc;
+    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18, in.Hs, in.Ws)) return rc;
     TcPatchParams pp;
     memset(&pp, 0, sizeof pp);
     pp.njobs = L.njobs;
@@ -511,7 +531,8 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       // stride-2 convolutions read one patch per (input-row parity, inner offset) of the parity view; every patch starts one
       // view row above the tile.  conv2: steps (kernel row a, column pair jj), rows a = 0,2,4 read row parity 1, rows 1,3
       // parity 0; jj = -1 only uses the upper half of its K slab.  conv8: (row parity, column parity) = four patches.
-      const TcJob& src = L.jobs[0];
+      TcJob src;
+      { int o_, pby, pbx; same_pad(in.H, sp.k, sp.s, o_, pby); same_pad(in.W, sp.k, sp.s, o_, pbx); build_s2_program(sp, pby, pbx, src); }
       TcPatchJob& dst = pp.jobs[0];
       dst.nsteps = src.nsteps; dst.nchains = 0; dst.out_oy = 0; dst.out_ox = 0;
       pp.npatch = 0;
@@ -542,6 +563,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       }
     }
     pp.P = P; pp.n_split = n_split; pp.Hp = Hp; pp.Wp = Wp; pp.Ho = Ho; pp.Wo = Wo; pp.out_stride = L.out_stride;
+    // storage extents of the split output (and of the residual, which shares them); fp32 / latent outputs are dense
+    pp.Hs = out_mode == TC_OUT_SPLIT ? out.Hs : Ho; pp.Ws = out_mode == TC_OUT_SPLIT ? out.Ws : Wo;
+    if (res && (res->Hs != out.Hs || res->Ws != out.Ws)) return fail(h, NNIC_ERR_CUDA, "internal: residual and output storage differ");
     pp.rows_per_set = L.rows_per_set;
     pp.inv_scale[0] = L.inv_scale[0]; pp.inv_scale[1] = L.inv_scale[1];
     pp.bias = L.bias;
@@ -601,14 +625,26 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
   same_pad(H, 5, 2, H1, t); same_pad(W, 5, 2, W1, t);
   same_pad(H1, 5, 2, H2, t); same_pad(W1, 5, 2, W2, t);
   same_pad(H2, 5, 2, H3, t); same_pad(W2, 5, 2, W3, t);
-  const size_t need = act_bytes(split, P, H1, W1, 32) + 3 * act_bytes(split, P, H2, W2, 64) +
+  const size_t need = act_bytes(split, P, even_up(H1), even_up(W1), 32) + 3 * act_bytes(split, P, even_up(H2), even_up(W2), 64) +
                       (split ? 0 : act_bytes(false, P, H3, W3, 32)) + 8192;
   size_t base_used = h->arena_used;
   if (h->arena.bytes < base_used + need) return fail(h, NNIC_ERR_CUDA, "internal: arena too small (%zu < %zu)", h->arena.bytes, base_used + need);
-  Act a1 = take_act(h, split, P, H1, W1, 32);
-  Act a2 = take_act(h, split, P, H2, W2, 64);
-  Act a3 = take_act(h, split, P, H2, W2, 64);
-  Act a4 = take_act(h, split, P, H2, W2, 64);
+  // conv2 and conv8 read a1 / a4 through parity views: even storage (a2, a3 share a4's layout: a2 is its residual)
+  const bool even = split && h->tc_conv1;
+  Act a1 = take_act(h, split, P, H1, W1, 32, even);
+  Act a2 = take_act(h, split, P, H2, W2, 64, even);
+  Act a3 = take_act(h, split, P, H2, W2, 64, even);
+  Act a4 = take_act(h, split, P, H2, W2, 64, even);
+  if (split && !even && ((H1 | W1 | H2 | W2) & 1))
+    return fail(h, NNIC_ERR_SHAPE, "NNIC_TC_CONV1=0 (development) only supports sizes that are multiples of 8");
+  if (a1.Hs != H1 || a1.Ws != W1) {             // the padding row / column must read as zeros
+    CK(h, cudaMemsetAsync(a1.hi, 0, (size_t)P * a1.Hs * a1.Ws * 32 * 2, st));
+    CK(h, cudaMemsetAsync(a1.lo, 0, (size_t)P * a1.Hs * a1.Ws * 32 * 2, st));
+  }
+  if (a4.Hs != H2 || a4.Ws != W2) {
+    CK(h, cudaMemsetAsync(a4.hi, 0, (size_t)P * a4.Hs * a4.Ws * 64 * 2, st));
+    CK(h, cudaMemsetAsync(a4.lo, 0, (size_t)P * a4.Hs * a4.Ws * 64 * 2, st));
+  }
   Act a5; a5.H = H3; a5.W = W3; a5.C = 32;
   if (split && h->tc_conv1) {
     TcConv1Params cp;
@@ -619,7 +655,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
     cp.w_hi = h->c1_w_hi; cp.w_lo = h->c1_w_lo; cp.bias = h->c1_bias;
     cp.inv_scale[0] = h->c1_inv_scale[0]; cp.inv_scale[1] = h->c1_inv_scale[1];
     cp.cc = colour_consts();
-    cp.out_hi = a1.hi; cp.out_lo = a1.lo;
+    cp.out_hi = a1.hi; cp.out_lo = a1.lo; cp.Hs = a1.Hs; cp.Ws = a1.Ws;
     CKL(h, K_CONV1, st, launch_tc_conv1(cp, h->num_sms, h->error_flag_dev, st));
   } else {
     CKL(h, K_CONV1, st, launch_conv1(rgb, planes, nb, H, W, h->w_edge[0].data(), h->b_edge[0].data(), a1.hi, a1.lo, a1.f32, st));
@@ -678,8 +714,8 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (split && h->tc_dconv8) {
     CUtensorMap ma_hi, ma_lo;
-    if (int rc = make_act_map(h, &ma_hi, d4.hi, P, 4 * lh, 4 * lw, 64, false, 64, 128)) return rc;
-    if (int rc = make_act_map(h, &ma_lo, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128)) return rc;
+    if (int rc = make_act_map(h, &ma_hi, d4.hi, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
+    if (int rc = make_act_map(h, &ma_lo, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
     TcDconv8Params dp;
     memset(&dp, 0, sizeof dp);
     dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
@@ -702,23 +738,12 @@ size_t enc_act_need(bool split, size_t P, int H, int W) {
   same_pad(H, 5, 2, H1, t); same_pad(W, 5, 2, W1, t);
   same_pad(H1, 5, 2, H2, t); same_pad(W1, 5, 2, W2, t);
   same_pad(H2, 5, 2, H3, t); same_pad(W2, 5, 2, W3, t);
-  return act_bytes(split, P, H1, W1, 32) + 3 * act_bytes(split, P, H2, W2, 64) + act_bytes(false, P, H3, W3, 32) + 16384;
+  return act_bytes(split, P, even_up(H1), even_up(W1), 32) + 3 * act_bytes(split, P, even_up(H2), even_up(W2), 64) +
+         act_bytes(false, P, H3, W3, 32) + 16384;
 }
 size_t dec_act_need(bool split, size_t P, int lh, int lw) {
   return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
 }
-
-// The tensor-core kernels read stride-2 inputs through parity views, which need even sizes at every stage, i.e. H and W
-// multiples of 8.  Other sizes (TF SAME padding then pads (2,2) instead of (1,2)) run the same call through the fp32 FFMA
-// kernels -- still on the GPU, same results within the parity tolerance, several times slower.  The guard restores the
-// handle's arithmetic when the call returns.
-struct ArithForShape {
-  nnic_t* h; int saved;
-  ArithForShape(nnic_t* h_, int H, int W) : h(h_), saved(h_->arith) {
-    if (h->arith == NNIC_ARITH_TC_SPLIT && (H % 8 != 0 || W % 8 != 0)) h->arith = NNIC_ARITH_SIMT_F32;
-  }
-  ~ArithForShape() { h->arith = saved; }
-};
 
 }  // namespace
 
@@ -839,7 +864,6 @@ static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8
   if (!rgb || !latent) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: non-positive shape %dx%dx%d", N, H, W);
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
-  ArithForShape arith_guard(h, H, W);
   DeviceGuard g(h->device);
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -954,7 +978,6 @@ int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W,
   if (!h) return NNIC_ERR_INVALID_ARG;
   if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_encoder_planes: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
-  ArithForShape arith_guard(h, H, W);
   DeviceGuard g(h->device);
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;

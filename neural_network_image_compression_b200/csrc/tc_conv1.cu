@@ -300,7 +300,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       // 16 channels = 32 bytes per fp16 plane: one 256-bit store each (a full sector per thread)
       const int y = it.ty * kTileRows + my, x = it.tx * kTileCols + mx;
       if (y < Ho && x < Wo) {
-        const size_t o = (((size_t)p * Ho + y) * Wo + x) * CO + ch0;
+        const size_t o = (((size_t)p * prm.Hs + y) * prm.Ws + x) * CO + ch0;
         st_global_v8(prm.out_hi + o, h);
         st_global_v8(prm.out_lo + o, l);
       }

@@ -307,7 +307,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int oY = tY0 + lg * 4 + (lane >> 3), oX = tX0 + (lane & 7);
         const int ooy = oY * prm.out_stride + prm.jobs[j].out_oy, oox = oX * prm.out_stride + prm.jobs[j].out_ox;
         const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo;
-        const size_t ooff = (((size_t)p * prm.Ho + ooy) * prm.Wo + oox) * COUT + ch0;
+        const size_t ooff = (((size_t)p * prm.Hs + ooy) * prm.Ws + oox) * COUT + ch0;
         // residual: loaded now so that its latency hides behind the MMAs
         uint32_t res_h[HALF / 2], res_l[HALF / 2];
         const bool has_res = prm.res_hi != nullptr;
