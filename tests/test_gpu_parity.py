@@ -384,14 +384,14 @@ def test_compress_uncompress_directories(nn, codec_factory, tmp_path):
     assert np.array_equal(nn.unpack_latent(small[None]), enc(synthetic_images(1, 32, 48, seed=32)))
 
 
-@pytest.mark.parametrize("shape", [(3, 72, 40), (1, 8, 8), (2, 136, 264)])
+@pytest.mark.parametrize("shape", [(3, 72, 40), (1, 8, 8), (2, 136, 264), (2, 45, 67)])
 def test_outputs_stay_inside_their_buffers(nn, codec_factory, shape):
     """Every output is placed in the middle of a larger sentinel-filled device buffer: the kernels (partial tiles at
     the right / bottom edge, 256-bit stores, the histogram flush) must not write one byte outside it."""
     import torch
     enc, dec = codec_factory("spread", "tc_split")
     n, hh, ww = shape
-    lh, lw = hh // 8, ww // 8
+    lh, lw = -(-hh // 8), -(-ww // 8)
     x = torch.from_numpy(synthetic_images(n, hh, ww, seed=41)).cuda()
     guard = 4096
 
@@ -401,9 +401,9 @@ def test_outputs_stay_inside_their_buffers(nn, codec_factory, shape):
 
     big_lat, lat = framed(n * lh * lw * 96, torch.uint8, 0xA5)
     big_pre, pre = framed(n * lh * lw * 96, torch.float32, -7.0)
-    big_rgb, rgb = framed(n * hh * ww * 3, torch.uint8, 0x5A)
+    big_rgb, rgb = framed(n * 8 * lh * 8 * lw * 3, torch.uint8, 0x5A)
     big_hg, hg = framed(3 * 256, torch.int64, -1)
-    lat = lat.view(n, lh, lw, 96); rgb = rgb.view(n, hh, ww, 3)
+    lat = lat.view(n, lh, lw, 96); rgb = rgb.view(n, 8 * lh, 8 * lw, 3)
     hg.zero_()
     hg = hg.view(3, 256)
     # nnic_encode with the optional pre-quantisation output, then the fused encode + rate, then decode
