@@ -518,7 +518,7 @@ def test_cluster_multicast_variant_is_bit_identical(nn, monkeypatch):
     enc0, dec0 = codec()
     monkeypatch.setenv("NNIC_TC_CLUSTER", "2")
     enc1, dec1 = codec()
-    for shape in ((1, 8, 8), (1, 72, 40), (3, 136, 264), (5, 64, 96)):
+    for shape in ((1, 8, 8), (1, 72, 40), (3, 136, 264), (5, 64, 96), (2, 45, 67)):
         img = synthetic_images(*shape, seed=71)
         sym0, r0 = enc0.encode_rate(img)
         sym1, r1 = enc1.encode_rate(img)
