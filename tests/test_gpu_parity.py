@@ -589,3 +589,64 @@ def test_device_calls_can_be_captured_in_a_cuda_graph(nn, codec_factory):
         assert np.array_equal(rgb.cpu().numpy(), dec(want_lat))
         assert np.array_equal(r.hist.cpu().numpy().astype(np.int64), O.histogram(want_lat))
         assert np.array_equal(hg.cpu().numpy(), O.histogram(want_lat).sum(axis=0))
+
+
+def test_c_program_on_the_abi_matches_the_python_layer(nn, tmp_path):
+    """examples/c_abi_demo.c drives libnnic.so from plain C with host buffers (nnic_create, nnic_set_weights,
+    nnic_encode_rate, nnic_decode).  The test rebuilds its LCG weights and image in Python and expects the same latent and
+    reconstruction bytes (FNV-1a), bpp and symbol count."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "neural_network_image_compression_b200")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_demo.c"),
+                    "-L", lib_dir, "-lnnic", f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = dict(re.findall(r"(latent_fnv|recon_fnv) ([0-9a-f]{16})", out.stdout))
+    bpp_c = [float(v) for v in re.search(r"bpp (\S+) (\S+)", out.stdout).groups()]
+
+    state = 12345
+
+    def draws(n):                                   # the program's LCG: float32((state >> 8) * 2^-24)
+        nonlocal state
+        vals = np.empty(n, np.float32)
+        for i in range(n):
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            vals[i] = np.float32(state >> 8) * np.float32(1.0 / 16777216.0)
+        return vals
+    enc_l = ((5, 1, 32), (5, 32, 64), (3, 64, 64), (3, 64, 64), (5, 64, 32))
+    dec_l = ((5, 32, 64), (3, 64, 64), (3, 64, 64), (5, 64, 64), (5, 64, 1))
+    sets = []
+    for s in range(4):
+        w = {}
+        names = [layer[0] for layer in nn.weights.layers_of("encoder" if s < 2 else "decoder")]
+        for name, (k, cin, cout) in zip(names, enc_l if s < 2 else dec_l):
+            limit = np.float32(1.6) * np.sqrt(np.float32(6.0) / np.float32((cin + cout) * k * k)).astype(np.float32)
+            kern = (np.float32(2.0) * draws(k * k * cin * cout) - np.float32(1.0)) * limit
+            w[name + "/kernel"] = kern.reshape((k, k, cin, cout) if s < 2 else (k, k, cout, cin)).astype(np.float32)
+            w[name + "/bias"] = ((np.float32(2.0) * draws(cout) - np.float32(1.0)) * np.float32(0.05)).astype(np.float32)
+        sets.append(w)
+    n_, h_, w_ = 2, 64, 96
+    img = np.empty((n_, h_, w_, 3), np.uint8)
+    for n in range(n_):
+        for y in range(h_):
+            for x in range(w_):
+                for c in range(3):
+                    state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+                    u = float(np.float32(state >> 8) * np.float32(1.0 / 16777216.0))
+                    img[n, y, x, c] = int(128.0 + 100.0 * np.sin(0.11 * x + 0.07 * y * (c + 1) + n) + 20.0 * u) & 0xFF
+    enc, dec = nn.Encoder(0), nn.Decoder(0)
+    enc.set_weights(0, sets[0]); enc.set_weights(1, sets[1]); dec.set_weights(0, sets[2]); dec.set_weights(1, sets[3])
+    lat, r = enc.encode_rate(img)
+    rec = dec(lat)
+
+    def fnv(a):
+        hsh = 1469598103934665603
+        for b in a.tobytes():
+            hsh = ((hsh ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return f"{hsh:016x}"
+    assert got["latent_fnv"] == fnv(lat) and got["recon_fnv"] == fnv(rec)
+    assert np.allclose(bpp_c, r.bpp, atol=1e-6)

@@ -249,3 +249,12 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "MP/s" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_c_example_compiles_as_pedantic_c99(tmp_path):
+    """examples/c_abi_demo.c (run on the GPU by tests/test_gpu_parity.py) builds against the header and the library."""
+    lib_dir = os.path.dirname(LIB)
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.dirname(HEADER),
+                        os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", lib_dir, "-lnnic", f"-Wl,-rpath,{lib_dir}", "-lm",
+                        "-o", str(tmp_path / "demo")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
