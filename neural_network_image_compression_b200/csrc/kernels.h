@@ -12,6 +12,17 @@
 
 namespace nnic {
 
+// Kernel attributes (opt-in shared memory size) are per device: true the first time it is called on the current device.
+inline bool first_use_on_device(unsigned long long& seen_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen_mask & bit) return false;
+  seen_mask |= bit;
+  return true;
+}
+
+
 struct ColourConsts {
   float k[3][3];     // RGB -> YCbCr rows   (float)(ycbcr_kernel)      utils.py:7
   float kinv[3][3];  // YCbCr -> RGB rows   (float)(inv(ycbcr_kernel)) utils.py:8

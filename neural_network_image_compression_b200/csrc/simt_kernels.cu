@@ -427,12 +427,11 @@ cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float*
   Dconv8Weights wp;
   memcpy(wp.w, w, sizeof wp.w);
   wp.b[0] = bias[0]; wp.b[1] = bias[1];
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(k_dconv8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, D8_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dconv8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, D8_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (in_hi) k_dconv8<true><<<grid, block, D8_SMEM, stream>>>(in_hi, in_lo, nullptr, N, Hi, Wi, wp, rgb, prequant, planes, cc);
   else k_dconv8<false><<<grid, block, D8_SMEM, stream>>>(nullptr, nullptr, in_f32, N, Hi, Wi, wp, rgb, prequant, planes, cc);

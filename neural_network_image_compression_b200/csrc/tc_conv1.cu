@@ -333,12 +333,11 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
 }  // namespace
 
 cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_flag, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(k_tc_conv1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_conv1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int tiles_x = (prm.Wo + kTileCols - 1) / kTileCols, tiles_y = (prm.Ho + kTileRows - 1) / kTileRows;
   const long long tiles = (long long)tiles_x * tiles_y * 3 * prm.N;

@@ -451,8 +451,12 @@ static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap&
                                      cudaStream_t stream) {
   using Cfg = PCfg<RB, NSPLIT, COUT>;
   auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL>;
-  static int max_grid = 0;                     // CTAs that can be co-resident (persistent kernel: one wave)
-  if (!max_grid) {
+  static unsigned long long attr_devices = 0;
+  static int max_grid_of[64];                  // per device: CTAs that can be co-resident (persistent kernel: one wave)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& max_grid = max_grid_of[dev & 63];
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     max_grid = num_sms;

@@ -275,11 +275,10 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 cudaError_t launch_tc_dconv8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                              const CUtensorMap& w_lo, const TcDconv8Params& prm, int num_sms, int* error_flag,
                              cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_use_on_device(attr_devices)) {
     cudaError_t e = cudaFuncSetAttribute(k_tc_dconv8, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int tiles_x = (prm.Wi + IW - 1) / IW, tiles_y = (prm.Hi + IH - 1) / IH;
   const long long items = (long long)tiles_x * tiles_y * prm.N;

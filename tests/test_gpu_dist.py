@@ -70,3 +70,26 @@ def test_c_abi_hist_allreduce_over_nccl(nn):
     finally:
         for d in range(ndev):
             nccl.ncclCommDestroy(C.c_void_p(comms[d]))
+
+
+def test_one_process_drives_two_gpus(nn):
+    """One handle per GPU inside ONE process (SURVEY.md 8b threading row): the same weights and images give the same
+    bytes on every device; kernel attributes and tensor maps are set up per device."""
+    import torch
+    from conftest import make_weights, synthetic_images
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    eY, eC, dY, dC = make_weights("spread")
+    img = synthetic_images(3, 72, 104, seed=91)
+    outs = []
+    for dev in (1, 0, 1):
+        enc, dec = nn.Encoder(dev), nn.Decoder(dev)
+        enc.set_weights(0, eY); enc.set_weights(1, eC); dec.set_weights(0, dY); dec.set_weights(1, dC)
+        lat, r = enc.encode_rate(img)
+        x = torch.from_numpy(img).cuda(dev)
+        lat_d = enc(x)
+        assert lat_d.device.index == dev and np.array_equal(lat_d.cpu().numpy(), lat)
+        outs.append((lat, r.hist.copy(), dec(lat)))
+    for lat, hist, rec in outs[1:]:
+        assert np.array_equal(lat, outs[0][0]) and np.array_equal(hist, outs[0][1]) and np.array_equal(rec, outs[0][2])
+    assert np.array_equal(outs[0][1].astype(np.int64), O.histogram(outs[0][0]))
