@@ -26,10 +26,14 @@ class Decoder(ProClass):
             import torch
             if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 96 or not x.is_cuda:
                 raise ValueError("expected a CUDA uint8 tensor [N,h,w,96]")
+            if x.device.index != self.device or (out is not None and (not out.is_cuda or out.device != x.device)):
+                raise ValueError(f"tensors must live on the handle's GPU (cuda:{self.device})")
             x = x.contiguous()
             n, lh, lw, _ = x.shape
             if out is None:
                 out = torch.empty((n, 8 * lh, 8 * lw, 3), dtype=torch.uint8, device=x.device)
+            elif tuple(out.shape) != (n, 8 * lh, 8 * lw, 3) or out.dtype != torch.uint8 or not out.is_contiguous():
+                raise ValueError("out has the wrong shape, dtype or layout")
             pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
             self.handle.check(lib.nnic_decode(h, _ptr(x), n, lh, lw, _ptr(out), _ptr(pre), MEM_DEVICE,
                                               _stream_of(x)), "nnic_decode")

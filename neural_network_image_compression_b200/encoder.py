@@ -21,10 +21,14 @@ class Encoder(ProClass):
             import torch
             if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3 or not x.is_cuda:
                 raise ValueError("expected a CUDA uint8 tensor [N,H,W,3]")
+            if x.device.index != self.device or (out is not None and (not out.is_cuda or out.device != x.device)):
+                raise ValueError(f"tensors must live on the handle's GPU (cuda:{self.device})")
             x = x.contiguous()
             n, hh, ww, _ = x.shape
             if out is None:
                 out = torch.empty((n, -(-hh // 8), -(-ww // 8), 96), dtype=torch.uint8, device=x.device)
+            elif tuple(out.shape) != (n, -(-hh // 8), -(-ww // 8), 96) or out.dtype != torch.uint8 or not out.is_contiguous():
+                raise ValueError("out has the wrong shape, dtype or layout")
             pre = torch.empty(out.shape, dtype=torch.float32, device=x.device) if return_prequant else None
             self.handle.check(lib.nnic_encode(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(pre), MEM_DEVICE,
                                               _stream_of(x)), "nnic_encode")
@@ -57,11 +61,15 @@ class Encoder(ProClass):
             import torch
             if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3 or not x.is_cuda:
                 raise ValueError("expected a CUDA uint8 tensor [N,H,W,3]")
+            if x.device.index != self.device or (out is not None and (not out.is_cuda or out.device != x.device)):
+                raise ValueError(f"tensors must live on the handle's GPU (cuda:{self.device})")
             x = x.contiguous()
             n, hh, ww, _ = x.shape
             dev = x.device
             if out is None:
                 out = torch.empty((n, -(-hh // 8), -(-ww // 8), 96), dtype=torch.uint8, device=dev)
+            elif tuple(out.shape) != (n, -(-hh // 8), -(-ww // 8), 96) or out.dtype != torch.uint8 or not out.is_contiguous():
+                raise ValueError("out has the wrong shape, dtype or layout")
             hist = torch.empty((n, 3, 256), dtype=torch.int32, device=dev)
             ent = torch.empty((n, 3), dtype=torch.float32, device=dev)
             bpp = torch.empty((n,), dtype=torch.float32, device=dev)

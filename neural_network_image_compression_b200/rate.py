@@ -29,6 +29,8 @@ def rate(handle: Handle, latent, H: int | None = None, W: int | None = None, his
     W = 8 * lw if W is None else int(W)
     if _is_torch(latent):
         import torch
+        if not latent.is_cuda or latent.device.index != handle.device:
+            raise ValueError(f"latent must live on the handle's GPU (cuda:{handle.device})")
         latent = latent.contiguous()
         dev = latent.device
         hist = torch.empty((n, 3, 256), dtype=torch.int32, device=dev)

@@ -93,3 +93,9 @@ def test_one_process_drives_two_gpus(nn):
     for lat, hist, rec in outs[1:]:
         assert np.array_equal(lat, outs[0][0]) and np.array_equal(hist, outs[0][1]) and np.array_equal(rec, outs[0][2])
     assert np.array_equal(outs[0][1].astype(np.int64), O.histogram(outs[0][0]))
+    enc0 = nn.Encoder(0)
+    enc0.set_weights(0, eY); enc0.set_weights(1, eC)
+    with pytest.raises(ValueError, match="handle's GPU"):
+        enc0(torch.from_numpy(img).cuda(1))
+    with pytest.raises(ValueError, match="handle's GPU"):
+        nn.rate(enc0.handle, torch.from_numpy(outs[0][0]).cuda(1))

@@ -244,6 +244,30 @@ def test_argument_errors(nn, codec_factory):
         enc(np.zeros((1, 8, 8, 3), np.float32))
     with pytest.raises(ValueError):
         dec(np.zeros((1, 2, 2, 32), np.uint8))
+    import torch
+    xt = torch.zeros((2, 16, 24, 3), dtype=torch.uint8, device="cuda")
+    for bad in (torch.empty((2, 2, 3, 32), dtype=torch.uint8, device="cuda"), torch.empty((2, 2, 3, 96), dtype=torch.float32, device="cuda"),
+                torch.empty((2, 2, 3, 192), dtype=torch.uint8, device="cuda")[..., ::2]):
+        with pytest.raises(ValueError):
+            enc(xt, out=bad)
+        with pytest.raises(ValueError):
+            enc.encode_rate(xt, out=bad)
+    with pytest.raises(ValueError):
+        dec(torch.zeros((2, 2, 3, 96), dtype=torch.uint8, device="cuda"), out=torch.empty((2, 16, 24, 4), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        enc(torch.zeros((2, 16, 24, 3), dtype=torch.uint8))          # a CPU tensor is not silently copied
+    # replacing the weights of a handle that has already run takes effect on the next call
+    img = synthetic_images(1, 32, 48, seed=13)
+    sY, sC, _d2, _d3 = make_weights("spread")
+    eY2, eC2, _d0, _d1 = make_weights("default")
+    own = nn.Encoder(0)
+    own.set_weights(0, sY); own.set_weights(1, sC)
+    before = own(img)
+    own.set_weights(0, eY2); own.set_weights(1, eC2)
+    after = own(img)
+    assert not np.array_equal(before, after) and np.array_equal(after, enc(img))
+    own.set_weights(0, sY); own.set_weights(1, sC)
+    assert np.array_equal(own(img), before)
     fresh = nn.Encoder(0)
     with pytest.raises(nn.NnicError, match="not set"):
         fresh(np.zeros((1, 8, 8, 3), np.uint8))
