@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nnic.h"
@@ -745,6 +747,21 @@ size_t dec_act_need(bool split, size_t P, int lh, int lw) {
   return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
 }
 
+// NNIC_MEM_DEVICE buffers must be device (or managed) memory of the handle's GPU: a host pointer or another GPU's memory
+// would fault inside a kernel, so it is rejected before anything is enqueued.  NULL (optional outputs) passes.
+int check_device_ptrs(nnic_t* h, int mem_kind, std::initializer_list<std::pair<const char*, const void*>> ptrs) {
+  if (mem_kind != NNIC_MEM_DEVICE) return 0;
+  for (const auto& np : ptrs) {
+    if (!np.second) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, np.second) != cudaSuccess) { cudaGetLastError(); return fail(h, NNIC_ERR_INVALID_ARG, "%s: not a CUDA pointer", np.first); }
+    if (at.type == cudaMemoryTypeManaged) continue;
+    if (at.type != cudaMemoryTypeDevice || at.device != h->device)
+      return fail(h, NNIC_ERR_INVALID_ARG, "%s: NNIC_MEM_DEVICE buffers must be device memory of GPU %d", np.first, h->device);
+  }
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -865,6 +882,7 @@ static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode: non-positive shape %dx%dx%d", N, H, W);
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"rgb", rgb}, {"latent", latent}, {"prequant", prequant}})) return rc;
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -926,6 +944,7 @@ int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t
   if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_decode: non-positive shape %dx%dx%d", N, lh, lw);
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"latent", latent}, {"rgb", rgb}, {"prequant", prequant}})) return rc;
   if (int rc = finalize_weights(h, 1)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -979,6 +998,7 @@ int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W,
   if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_encoder_planes: NULL buffer");
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"planes", planes}, {"out", out}})) return rc;
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -1009,6 +1029,7 @@ int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int l
   if (!planes || !out) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_run_decoder_planes: NULL buffer");
   if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"planes", planes}, {"out", out}})) return rc;
   if (int rc = finalize_weights(h, 1)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -1086,6 +1107,8 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
   if (N <= 0 || lh <= 0 || lw <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_rate: non-positive shape");
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"latent", latent}, {"hist", hist}, {"entropy_bits", entropy_bits}, {"bpp", bpp},
+                                               {"hist_global", hist_global}})) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool host = mem_kind == NNIC_MEM_HOST;
   const size_t lat_bytes = (size_t)N * lh * lw * 96;
@@ -1106,6 +1129,8 @@ int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_encode_rate: non-positive shape %dx%dx%d", N, H, W);
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"hist", hist}, {"entropy_bits", entropy_bits}, {"bpp", bpp}, {"hist_global", hist_global}}))
+    return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool host = mem_kind == NNIC_MEM_HOST;
   RateBufs rb;
@@ -1129,6 +1154,7 @@ int nnic_hist_allreduce(nnic_t* h, void* nccl_comm, uint64_t* hist_global, void*
     if (!fn) return fail(h, NNIC_ERR_CUDA, "nnic_hist_allreduce: NCCL (libnccl.so.2) is not available in this process");
   }
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, NNIC_MEM_DEVICE, {{"hist_global", hist_global}})) return rc;
   constexpr int kNcclUint64 = 5, kNcclSum = 0;       // nccl.h: ncclDataType_t / ncclRedOp_t
   const int rc = fn(hist_global, hist_global, 768, kNcclUint64, kNcclSum, nccl_comm, (cudaStream_t)stream);
   if (rc != 0) return fail(h, NNIC_ERR_CUDA, "ncclAllReduce failed with ncclResult_t %d", rc);
@@ -1139,6 +1165,7 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
   if (!h) return NNIC_ERR_INVALID_ARG;
   if (!counts || !entropy_bits || rows <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_entropy_from_counts: bad argument");
   DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"counts", counts}, {"entropy_bits", entropy_bits}})) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (mem_kind == NNIC_MEM_DEVICE) {
     CKL(h, K_ENTROPY, st, launch_entropy_u64((const unsigned long long*)counts, rows, entropy_bits, st));

@@ -256,6 +256,12 @@ def test_argument_errors(nn, codec_factory):
         dec(torch.zeros((2, 2, 3, 96), dtype=torch.uint8, device="cuda"), out=torch.empty((2, 16, 24, 4), dtype=torch.uint8, device="cuda"))
     with pytest.raises(ValueError):
         enc(torch.zeros((2, 16, 24, 3), dtype=torch.uint8))          # a CPU tensor is not silently copied
+    # the C ABI rejects a host pointer passed as NNIC_MEM_DEVICE before anything is enqueued
+    hx = np.zeros((1, 16, 24, 3), np.uint8); hl = np.zeros((1, 2, 3, 96), np.uint8)
+    hnd = enc.handle
+    assert hnd.lib.nnic_encode(hnd.h, hx.ctypes.data, 1, 16, 24, hl.ctypes.data, None, 1, None) == -1
+    assert b"device memory" in hnd.lib.nnic_last_error(hnd.h) or b"CUDA pointer" in hnd.lib.nnic_last_error(hnd.h)
+    assert hnd.lib.nnic_rate(hnd.h, hl.ctypes.data, 1, 2, 3, 16, 24, None, None, None, None, 1, None) == -1
     # replacing the weights of a handle that has already run takes effect on the next call
     img = synthetic_images(1, 32, 48, seed=13)
     sY, sC, _d2, _d3 = make_weights("spread")
