@@ -420,7 +420,9 @@ def main():
             ach = FLOP_PER_PX[dom] * px / avg_ms / 1e9
             roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                         "frac": round(ach / peaks["tflops"], 4), "traffic": traffic.get(dom), "peak_source": peaks["source"],
-                        "note": "algorithmic FLOPs; the fp16 hi/lo split issues 3x as many tensor-core FLOPs"}
+                        "issued_tflops": round(3 * ach, 1), "issued_frac": round(3 * ach / peaks["tflops"], 4),
+                        "note": "achieved/frac count ALGORITHMIC FLOPs; the fp16 hi/lo split issues three fp16 products per "
+                                "MAC (issued_* = what the tensor pipe executes; ncu tensor-pipe activity in profiles/)"}
 
     # fingerprint of the all-rank symbol histogram of the last step: for the sharded workload it must not depend on --gpus
     hist_sha = None
