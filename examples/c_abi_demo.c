@@ -67,6 +67,24 @@ int main(void) {
          (unsigned long long)total, (unsigned long long)nnic_launch_count(h));
   printf("latent_fnv %016llx recon_fnv %016llx\n", (unsigned long long)fnv1a(latent, sizeof latent),
          (unsigned long long)fnv1a(rec, sizeof rec));
+  /* Second pass with the Keras-default networks a fresh Encoder() / Decoder() of the reference holds: nnic_init_random draws
+   * them inside the library (NumPy default_rng stream; seeds 11..14 are the parity tests' "default" weight sets), and the
+   * per-feature-channel table of nnic_rate_channels must add up to the per-plane counts. */
+  for (int set = 0; set < 4; ++set) CHECK(nnic_init_random(h, set, 11u + (uint64_t)set));
+  uint64_t hist_global2[3 * 256] = {0};
+  static uint64_t hist_ch[96 * 256];
+  CHECK(nnic_encode_rate(h, rgb, N, H, W, latent, NULL, NULL, bpp, hist_global2, NNIC_MEM_HOST, NULL));
+  CHECK(nnic_rate_channels(h, latent, N, H / 8, W / 8, hist_ch, NNIC_MEM_HOST, NULL));
+  CHECK(nnic_decode(h, latent, N, H / 8, W / 8, rec, NULL, NNIC_MEM_HOST, NULL));
+  int rows_ok = 1;
+  for (int p = 0; p < 3; ++p)
+    for (int b = 0; b < 256; ++b) {
+      uint64_t s = 0;
+      for (int c = 0; c < 32; ++c) s += hist_ch[(p * 32 + c) * 256 + b];
+      if (s != hist_global2[p * 256 + b]) rows_ok = 0;
+    }
+  printf("default_latent_fnv %016llx default_recon_fnv %016llx channel_rows_ok %d default_bpp %.6f %.6f\n",
+         (unsigned long long)fnv1a(latent, sizeof latent), (unsigned long long)fnv1a(rec, sizeof rec), rows_ok, bpp[0], bpp[1]);
   nnic_destroy(h);
-  return total == sizeof latent ? 0 : 2;
+  return total == sizeof latent && rows_ok ? 0 : 2;
 }

@@ -86,6 +86,20 @@ uint64_t nnic_launch_count(const nnic_t* h);
  * `bias` is [Cout].  The library keeps its own repacked copies. */
 int nnic_set_weights(nnic_t* h, int set, int layer, const float* kernel, const float* bias);
 
+/* Replaces: a freshly constructed Encoder() / Decoder() (encoder.py:34-36, decoder.py:35-37), whose Keras layers
+ * start from glorot-uniform kernels (limit sqrt(6 / ((Cin + Cout) * kh * kw))) and zero biases.
+ * nnic_init_random installs such a network as weight set `set`.  The stream is NumPy's default_rng(seed) (PCG64 seeded
+ * through SeedSequence), i.e. bit-identical to neural_network_image_compression_b200/weights.py::glorot_uniform(kind, seed)
+ * -- the weight sets the oracle and the golden vectors use (seeds 11, 12, 13, 14 for the four sets).
+ * nnic_init_random_scaled multiplies the kernels by `gain` and draws biases from U(-bias_range, bias_range)
+ * (bias_range = 0: zero biases): the "spread" sets of the parity tests are (1.6, 0.05).
+ * nnic_glorot_uniform fills caller buffers instead (no handle, no GPU): the five kernels back to back in their Keras
+ * layouts, the five bias vectors back to back; nnic_layer_shape gives k, Cin, Cout of a layer. */
+int nnic_init_random(nnic_t* h, int set, uint64_t seed);
+int nnic_init_random_scaled(nnic_t* h, int set, uint64_t seed, double gain, double bias_range);
+int nnic_glorot_uniform(int set, uint64_t seed, double gain, double bias_range, float* kernels, float* biases);
+int nnic_layer_shape(int set, int layer, int* ksize, int* cin, int* cout);
+
 /* ---- encode ---------------------------------------------------------------------------------
  * Replaces: Encoder.__call__ (encoder.py:38-47).
  *   rgb     uint8 [N,H,W,3], C-contiguous
@@ -132,6 +146,13 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
 int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t* latent, uint32_t* hist,
                      float* entropy_bits, float* bpp, uint64_t* hist_global, int mem_kind, void* stream);
 
+/* Optional finer table: symbol counts per latent FEATURE CHANNEL, summed over the N images (BASELINE.json north_star
+ * "per-channel latent histogram"; the reference's own histogram is the per-(image, plane) one of nnic_rate, and rows
+ * 32p .. 32p+31 of this table add up to hist_global[p]).
+ *   hist_channels  uint64 [96][256], ACCUMULATED into (caller zeroes it) */
+int nnic_rate_channels(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint64_t* hist_channels, int mem_kind,
+                       void* stream);
+
 /* Cross-rank sum of the global symbol counts: the path's only exchange step.
  *   nccl_comm    the caller's ncclComm_t for this rank (one rank per GPU)
  *   hist_global  DEVICE uint64 [3][256], summed in place over all ranks of the communicator
@@ -149,6 +170,9 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
  * Activation scratch is grown lazily and reused.  Images beyond `max_planes_in_flight` colour
  * planes are processed in micro-batches inside one call.  0 = library default. */
 int nnic_set_micro_batch(nnic_t* h, int max_images_in_flight);
+/* CUtensorMap encodes this handle has done since creation (activation views are cached per tensor and shape: a
+ * steady-state call encodes none). */
+uint64_t nnic_tensor_map_encodes(const nnic_t* h);
 size_t nnic_scratch_bytes(const nnic_t* h);
 
 /* ---- per-kernel timing -------------------------------------------------------------------------

@@ -8,9 +8,10 @@ from ._lib import Handle, NnicError, colour_constants, load_library
 from .decoder import Decoder
 from .encoder import Encoder
 from .container import get_bpp, pack_latent, read_dataset, save_img, unpack_latent
-from .rate import Rate, entropy_from_counts, rate
+from .graph import GraphCodec
+from .rate import Rate, entropy_from_counts, rate, rate_channels
 from .utils import ProClass
 
-__all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "Rate", "entropy_from_counts",
+__all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "rate_channels", "Rate", "entropy_from_counts", "GraphCodec",
            "weights", "dist", "container", "colour_constants", "load_library", "pack_latent", "unpack_latent", "read_dataset",
            "save_img", "get_bpp"]

@@ -27,12 +27,18 @@ SYMBOLS = (
     ("nnic_get_arith", C.c_int, (_vp,)),
     ("nnic_launch_count", C.c_uint64, (_vp,)),
     ("nnic_set_weights", C.c_int, (_vp, C.c_int, C.c_int, _vp, _vp)),
+    ("nnic_init_random", C.c_int, (_vp, C.c_int, C.c_uint64)),
+    ("nnic_init_random_scaled", C.c_int, (_vp, C.c_int, C.c_uint64, C.c_double, C.c_double)),
+    ("nnic_glorot_uniform", C.c_int, (C.c_int, C.c_uint64, C.c_double, C.c_double, _vp, _vp)),
+    ("nnic_layer_shape", C.c_int, (C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))),
     ("nnic_encode", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp)),
     ("nnic_decode", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp)),
     ("nnic_run_encoder_planes", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_run_decoder_planes", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp)),
     ("nnic_encode_rate", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp)),
+    ("nnic_rate_channels", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
+    ("nnic_tensor_map_encodes", C.c_uint64, (_vp,)),
     ("nnic_hist_allreduce", C.c_int, (_vp, _vp, _vp, _vp)),
     ("nnic_set_decode_precision", C.c_int, (_vp, C.c_int)),
     ("nnic_get_decode_precision", C.c_int, (_vp,)),

@@ -66,8 +66,11 @@ cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t*
 
 // ---- rate ---------------------------------------------------------------------------------------
 // hist u32 [N][3][256] must be zeroed by the caller (launch_hist adds into it).
-cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist,
+cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, int num_sms, int variant,
                         cudaStream_t stream);
+// hist_ch u64 [96][256], added to: counts per latent feature channel over `total_pixels` latent pixels (all images)
+cudaError_t launch_hist_channels(const uint8_t* latent, size_t total_pixels, unsigned long long* hist_ch, int num_sms,
+                                 cudaStream_t stream);
 cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* hist_global,
                                cudaStream_t stream);
 // entropy[N][3] from hist u32; bpp[N] = sum_p entropy * symbols_per_plane / pixels  (optional)
@@ -105,6 +108,7 @@ struct TcPatchParams {
   int cout;                   // 64, or 32 (conv8)
   int fast;                   // one fp16 product per MAC, hi planes only (decoder, nnic_set_decode_precision)
   int cluster;                // 2: CTA pairs share every weight tile through TMA multicast; else 1
+  unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded (tc_common.cuh WaitCtx)
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;
@@ -136,6 +140,7 @@ struct TcConv1Params {
   const uint8_t* rgb;         // u8 [N,H,W,3] (colour transform fused), or
   const float* planes;        // f32 [3N,H,W,1]
   int N, H, W, Ho, Wo, pad_t, pad_l;
+  unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded
   int Hs, Ws;                 // storage rows / columns per plane of the output (>= Ho, Wo)
   const __half* w_hi;         // device [2 sets][32 channels][32 taps (25 used)] fp16, scaled
   const __half* w_lo;
@@ -152,6 +157,7 @@ cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_fl
 struct TcDconv8Params {
   int N, Hi, Wi;              // images, input size (output is 2Hi x 2Wi)
   int fast;                   // activations as one fp16 plane: A_hi x [W_hi | W_lo] only
+  unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded
   float inv_scale[2];         // 2^-(ka+kw) per weight set
   float bias[2];
   ColourConsts cc;

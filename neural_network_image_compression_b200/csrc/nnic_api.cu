@@ -78,6 +78,19 @@ struct nnic_handle {
   int tc_cluster = 0;               // weight tiles multicast to CTA pairs: NNIC_TC_CLUSTER=0 never, 1 residual layers, 2 all
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   EncodeTiledFn encode_tiled = nullptr;
+  unsigned long long wait_timeout = 4000000000ull;   // barrier-wait bound in SM cycles (NNIC_TC_TIMEOUT_MS, 0 = none)
+  int hist_variant = 0;             // NNIC_HIST_VARIANT (development): copies * 100 + blocks per SM of k_hist
+  int tc_dbg = 0;                   // development switches (NNIC_TC_DBG), read once in nnic_create
+  bool tc_prof = false;             // NNIC_TC_PROF: print the in-kernel role timers of a -DNNIC_TC_TIMERS build
+  long long* tc_prof_buf = nullptr; // [num_sms][4][8], per handle
+  // CUtensorMaps of the activation views, keyed by (layer slot, base pointers, shape): scratch addresses repeat from call
+  // to call, so a steady-state call encodes no tensor map at all (config 1 is 13 launches in ~0.25 ms: host work counts)
+  struct MapKey { int slot; const void* hi; const void* lo; int P, H, W, C, Hs, Ws; bool parity;
+                  bool operator==(const MapKey& o) const { return slot == o.slot && hi == o.hi && lo == o.lo && P == o.P && H == o.H && W == o.W && C == o.C && Hs == o.Hs && Ws == o.Ws && parity == o.parity; } };
+  struct MapEntry { MapKey key; CUtensorMap hi, lo; };
+  std::vector<MapEntry> map_cache;
+  size_t map_cache_next = 0;
+  uint64_t map_cache_hits = 0, map_cache_misses = 0;
   int* error_flag_host = nullptr;   // mapped pinned; written by a kernel whose barrier wait timed out
   int* error_flag_dev = nullptr;
 
@@ -209,6 +222,26 @@ int make_act_map(nnic_t* h, CUtensorMap* map, const __half* base, int P, int H, 
   }
   cuuint32_t box[5] = {(cuuint32_t)kslab, (cuuint32_t)box_cols, 1, (cuuint32_t)box_rows, 1};
   return make_map(h, map, const_cast<__half*>(base), 5, dims, strides, box, row_bytes);
+}
+
+// both planes' views of one activation tensor, from the handle's cache when this (tensor, shape) was seen before
+int cached_act_maps(nnic_t* h, int slot, const CUtensorMap** hi, const CUtensorMap** lo, const __half* base_hi, const __half* base_lo,
+                    int P, int H, int W, int C, bool parity, int kslab, int row_bytes, int box_cols, int box_rows, int Hs, int Ws) {
+  const nnic_handle::MapKey key{slot, base_hi, base_lo, P, H, W, C, Hs, Ws, parity};
+  for (auto& e : h->map_cache)
+    if (e.key == key) { *hi = &e.hi; *lo = &e.lo; ++h->map_cache_hits; return 0; }
+  ++h->map_cache_misses;
+  constexpr size_t kCap = 64;
+  nnic_handle::MapEntry* slot_e;
+  if (h->map_cache.size() < kCap) { h->map_cache.emplace_back(); slot_e = &h->map_cache.back(); }
+  else { slot_e = &h->map_cache[h->map_cache_next]; h->map_cache_next = (h->map_cache_next + 1) % kCap; }
+  slot_e->key = key;
+  slot_e->key.slot = -1;                         // invalid until both maps are encoded
+  if (int rc = make_act_map(h, &slot_e->hi, base_hi, P, H, W, C, parity, kslab, row_bytes, box_cols, box_rows, Hs, Ws)) return rc;
+  if (int rc = make_act_map(h, &slot_e->lo, base_lo, P, H, W, C, parity, kslab, row_bytes, box_cols, box_rows, Hs, Ws)) return rc;
+  slot_e->key.slot = slot;
+  *hi = &slot_e->hi; *lo = &slot_e->lo;
+  return 0;
 }
 
 // ---- weight repacking ----------------------------------------------------------------------------
@@ -496,9 +529,15 @@ void record_dbg(nnic_t* h, int slot, const Act& a, int P) {
   h->dbg[slot] = {a.hi, a.lo, a.f32, (size_t)P * a.H * a.W * a.C};
 }
 
+// A tensor-core kernel whose barrier wait timed out writes a code into mapped host memory and traps.  The flag is read
+// after every host-buffer call and at the START of every later call (so callers of the asynchronous device-buffer
+// path see it too, next to the sticky CUDA error the trap leaves); reading it resets it.
 int check_device_error(nnic_t* h) {
-  if (h->error_flag_host && *h->error_flag_host != 0)
-    return fail(h, NNIC_ERR_CUDA, "tensor-core kernel barrier wait timed out (code %d)", *h->error_flag_host);
+  if (h->error_flag_host && *h->error_flag_host != 0) {
+    const int code = *h->error_flag_host;
+    *h->error_flag_host = 0;
+    return fail(h, NNIC_ERR_CUDA, "a tensor-core kernel of an earlier call timed out in a barrier wait (code %d); the CUDA context is unusable", code);
+  }
   return 0;
 }
 
@@ -521,10 +560,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
   }
   TcLayer& L = h->tc[net][gi];
   {
-    CUtensorMap pa_hi, pa_lo;
+    const CUtensorMap *pa_hi = nullptr, *pa_lo = nullptr;
     if (L.parity_view && ((in.Hs | in.Ws) & 1)) return fail(h, NNIC_ERR_CUDA, "internal: stride-2 input without even storage");
-    if (int rc = make_act_map(h, &pa_hi, in.hi, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18, in.Hs, in.Ws)) return rc;
-    if (int rc = make_act_map(h, &pa_lo, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18, in.Hs, in.Ws)) return rc;
+    if (int rc = cached_act_maps(h, net * 4 + gi, &pa_hi, &pa_lo, in.hi, in.lo, P, in.H, in.W, in.C, L.parity_view, L.kslab, L.row_bytes, 10, 18, in.Hs, in.Ws)) return rc;
     TcPatchParams pp;
     memset(&pp, 0, sizeof pp);
     pp.njobs = L.njobs;
@@ -580,24 +618,26 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
     pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
     pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
-    if (const char* env = getenv("NNIC_TC_DBG")) pp.dbg = atoi(env);
+    pp.dbg = h->tc_dbg;
+    pp.wait_timeout = h->wait_timeout;
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
-    static long long* prof_buf = nullptr;
-    const bool prof = getenv("NNIC_TC_PROF") != nullptr;
+    const bool prof = h->tc_prof;
+    const size_t prof_words = (size_t)h->num_sms * 4 * 8;
     if (prof) {
-      if (!prof_buf) cudaMalloc(&prof_buf, 148 * 4 * 8 * sizeof(long long));
-      cudaMemsetAsync(prof_buf, 0, 148 * 4 * 8 * sizeof(long long), st);
-      pp.dbg_buf = prof_buf;
+      if (!h->tc_prof_buf) CK(h, cudaMalloc(&h->tc_prof_buf, prof_words * sizeof(long long)));
+      CK(h, cudaMemsetAsync(h->tc_prof_buf, 0, prof_words * sizeof(long long), st));
+      pp.dbg_buf = h->tc_prof_buf;
     }
     CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st,
-        launch_tc_conv_patch(L.row_bytes, pa_hi, pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
+        launch_tc_conv_patch(L.row_bytes, *pa_hi, *pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
     if (prof) {
-      std::vector<long long> hb(148 * 4 * 8);
+      std::vector<long long> hb(prof_words);
       cudaStreamSynchronize(st);
-      cudaMemcpy(hb.data(), prof_buf, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaMemcpy(hb.data(), h->tc_prof_buf, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
       double a[4][8] = {};
-      for (int b = 0; b < 148; ++b) for (int r = 0; r < 4; ++r) for (int k = 0; k < 8; ++k) a[r][k] += hb[(b * 4 + r) * 8 + k] / 148.0;
+      const int nb_ = h->num_sms;
+      for (int b = 0; b < nb_; ++b) for (int r = 0; r < 4; ++r) for (int k = 0; k < 8; ++k) a[r][k] += hb[((size_t)b * 4 + r) * 8 + k] / (double)nb_;
       fprintf(stderr, "[tcprof %s] producer: total %.0f wait_patch_empty %.0f wait_w_empty %.0f | mmaA: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | "
               "mmaB: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | epi: total %.0f wait_full %.0f tmem+add %.0f out %.0f\n",
               spec_of(net * 2, l).name, a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[1][3], a[1][4], a[2][0], a[2][1], a[2][2], a[2][3], a[2][4],
@@ -608,7 +648,10 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
 }
 
 int pick_micro_batch(const nnic_t* h, int N, size_t pixels_per_image) {
-  if (h->micro_batch > 0) return h->micro_batch < N ? h->micro_batch : N;
+  if (h->micro_batch > 0) {                    // caller's override, under the same plane limit as the default
+    const int mb = h->micro_batch < 21845 ? h->micro_batch : 21845;
+    return mb < N ? mb : N;
+  }
   const size_t target = (size_t)16 << 20;   // ~16 MP of RGB pixels in flight
   size_t nb = target / (pixels_per_image ? pixels_per_image : 1);
   if (nb < 1) nb = 1;
@@ -657,6 +700,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
     cp.w_hi = h->c1_w_hi; cp.w_lo = h->c1_w_lo; cp.bias = h->c1_bias;
     cp.inv_scale[0] = h->c1_inv_scale[0]; cp.inv_scale[1] = h->c1_inv_scale[1];
     cp.cc = colour_consts();
+    cp.wait_timeout = h->wait_timeout;
     cp.out_hi = a1.hi; cp.out_lo = a1.lo; cp.Hs = a1.Hs; cp.Ws = a1.Ws;
     CKL(h, K_CONV1, st, launch_tc_conv1(cp, h->num_sms, h->error_flag_dev, st));
   } else {
@@ -681,7 +725,7 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
       a5 = take_act(h, false, P, H3, W3, 32);
       if (int rc = run_gemm_layer(h, 0, 3, a4, a5, nullptr, P, nb, TC_OUT_F32, nullptr, nullptr, nullptr, st)) return rc;
       CKL(h, K_QUANTISE, st, launch_quantise(a5.f32, nb, H3, W3, latent, prequant, st));
-      if (hist) CKL(h, K_HIST, st, launch_hist(latent, nb, (size_t)H3 * W3, hist, st));
+      if (hist) CKL(h, K_HIST, st, launch_hist(latent, nb, (size_t)H3 * W3, hist, h->num_sms, h->hist_variant, st));
     }
   }
   record_dbg(h, 0, a1, P); record_dbg(h, 1, a2, P); record_dbg(h, 2, a3, P); record_dbg(h, 3, a4, P);
@@ -715,24 +759,32 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (split && h->tc_dconv8) {
-    CUtensorMap ma_hi, ma_lo;
-    if (int rc = make_act_map(h, &ma_hi, d4.hi, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
-    if (int rc = make_act_map(h, &ma_lo, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
+    const CUtensorMap *ma_hi = nullptr, *ma_lo = nullptr;
+    if (int rc = cached_act_maps(h, 8, &ma_hi, &ma_lo, d4.hi, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
     TcDconv8Params dp;
     memset(&dp, 0, sizeof dp);
     dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
     dp.fast = h->decode_fp16 ? 1 : 0;
+    dp.wait_timeout = h->wait_timeout;
     dp.inv_scale[0] = h->d8_inv_scale[0]; dp.inv_scale[1] = h->d8_inv_scale[1];
     dp.bias[0] = h->b_edge[1][0]; dp.bias[1] = h->b_edge[1][1];
     dp.cc = colour_consts();
     dp.rgb = rgb; dp.prequant = prequant; dp.planes_out = out_planes;
-    CKL(h, K_DCONV8, st, launch_tc_dconv8(ma_hi, ma_lo, h->d8_map_w_hi, h->d8_map_w_lo, dp, h->num_sms, h->error_flag_dev, st));
+    CKL(h, K_DCONV8, st, launch_tc_dconv8(*ma_hi, *ma_lo, h->d8_map_w_hi, h->d8_map_w_lo, dp, h->num_sms, h->error_flag_dev, st));
   } else {
     CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
   }
   record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
   h->arena_used = base_used;
   return 0;
+}
+
+// after a failed host-buffer call: wait for everything the call enqueued (errors ignored: the call already failed)
+void drain_streams(nnic_t* h, cudaStream_t st) {
+  cudaStreamSynchronize(h->h2d_stream);
+  cudaStreamSynchronize(st);
+  cudaStreamSynchronize(h->d2h_stream);
+  cudaGetLastError();
 }
 
 size_t enc_act_need(bool split, size_t P, int H, int W) {
@@ -798,6 +850,14 @@ int nnic_create(int device, nnic_t** out) {
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env);
+  if (const char* env = getenv("NNIC_TC_DBG")) h->tc_dbg = atoi(env);
+  if (const char* env = getenv("NNIC_HIST_VARIANT")) h->hist_variant = atoi(env);
+  h->tc_prof = getenv("NNIC_TC_PROF") != nullptr;
+  if (const char* env = getenv("NNIC_TC_TIMEOUT_MS")) {          // 0: never trap (profilers, debuggers, MPS)
+    const double ms_ = atof(env);
+    h->wait_timeout = ms_ <= 0.0 ? 0ull : (unsigned long long)(ms_ * 2.0e6);   // SM cycles at ~2 GHz
+  }
+  h->map_cache.reserve(64);
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
   if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
@@ -824,7 +884,7 @@ void nnic_destroy(nnic_t* h) {
   }
   cudaFree(h->d8_w_hi); cudaFree(h->d8_w_lo);
   cudaFree(h->c1_w_hi); cudaFree(h->c1_w_lo); cudaFree(h->c1_bias);
-  cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr);
+  cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr); cudaFree(h->tc_prof_buf);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
@@ -852,6 +912,7 @@ int nnic_get_decode_precision(const nnic_t* h) { return h && h->decode_fp16 ? NN
 int nnic_get_arith(const nnic_t* h) { return h ? h->arith : NNIC_ERR_INVALID_ARG; }
 uint64_t nnic_launch_count(const nnic_t* h) { return h ? h->launches : 0; }
 int nnic_set_micro_batch(nnic_t* h, int n) { if (!h || n < 0) return NNIC_ERR_INVALID_ARG; h->micro_batch = n; return NNIC_OK; }
+uint64_t nnic_tensor_map_encodes(const nnic_t* h) { return h ? 2 * h->map_cache_misses : 0; }
 size_t nnic_scratch_bytes(const nnic_t* h) { return h ? h->arena.bytes + h->rate_scratch.bytes : 0; }
 
 void nnic_colour_constants(float* k9, float* kinv9, float* off3) {
@@ -883,6 +944,7 @@ static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
   if (int rc = check_device_ptrs(h, mem_kind, {{"rgb", rgb}, {"latent", latent}, {"prequant", prequant}})) return rc;
+  if (int rc = check_device_error(h)) return rc;
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -906,27 +968,34 @@ static int encode_impl(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8
       if (prequant) d_pre[s2] = (float*)arena_take(h, mb * lat_px * 96 * 4);
     }
   }
-  int idx = 0;
-  for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
-    const int nb = (N - i0) < mb ? (N - i0) : mb;
-    const uint8_t* src = rgb + (size_t)i0 * img_px * 3;
-    uint8_t* dst = latent + (size_t)i0 * lat_px * 96;
-    float* pre = prequant ? prequant + (size_t)i0 * lat_px * 96 : nullptr;
-    if (host) {
-      const int s2 = idx & 1;
-      if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));   // staging set s2 is drained
-      CK(h, cudaMemcpyAsync(d_rgb[s2], src, nb * img_px * 3, cudaMemcpyHostToDevice, h->h2d_stream));
-      CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
-      CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
-      if (int rc = encode_batch(h, d_rgb[s2], nullptr, nb, H, W, d_lat[s2], d_pre[s2], nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
-      CK(h, cudaEventRecord(h->ev_comp[s2], st));
-      CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
-      CK(h, cudaMemcpyAsync(dst, d_lat[s2], nb * lat_px * 96, cudaMemcpyDeviceToHost, h->d2h_stream));
-      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
-      CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
-    } else {
-      if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
+  auto run = [&]() -> int {
+    int idx = 0;
+    for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
+      const int nb = (N - i0) < mb ? (N - i0) : mb;
+      const uint8_t* src = rgb + (size_t)i0 * img_px * 3;
+      uint8_t* dst = latent + (size_t)i0 * lat_px * 96;
+      float* pre = prequant ? prequant + (size_t)i0 * lat_px * 96 : nullptr;
+      if (host) {
+        const int s2 = idx & 1;
+        if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));   // staging set s2 is drained
+        CK(h, cudaMemcpyAsync(d_rgb[s2], src, nb * img_px * 3, cudaMemcpyHostToDevice, h->h2d_stream));
+        CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
+        CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
+        if (int rc = encode_batch(h, d_rgb[s2], nullptr, nb, H, W, d_lat[s2], d_pre[s2], nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
+        CK(h, cudaEventRecord(h->ev_comp[s2], st));
+        CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
+        CK(h, cudaMemcpyAsync(dst, d_lat[s2], nb * lat_px * 96, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * lat_px * 96 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
+      } else {
+        if (int rc = encode_batch(h, src, nullptr, nb, H, W, dst, pre, nullptr, d_hist ? d_hist + (size_t)i0 * 768 : nullptr, st)) return rc;
+      }
     }
+    return 0;
+  };
+  if (int rc = run()) {
+    if (host) drain_streams(h, st);             // no copy into / out of the caller's buffers is left in flight
+    return rc;
   }
   if (host) { CK(h, cudaStreamSynchronize(h->d2h_stream)); CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
   return NNIC_OK;
@@ -945,6 +1014,7 @@ int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t
   if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
   DeviceGuard g(h->device);
   if (int rc = check_device_ptrs(h, mem_kind, {{"latent", latent}, {"rgb", rgb}, {"prequant", prequant}})) return rc;
+  if (int rc = check_device_error(h)) return rc;
   if (int rc = finalize_weights(h, 1)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -967,27 +1037,34 @@ int nnic_decode(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint8_t
       if (prequant) d_pre[s2] = (float*)arena_take(h, mb * img_px * 3 * 4);
     }
   }
-  int idx = 0;
-  for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
-    const int nb = (N - i0) < mb ? (N - i0) : mb;
-    const uint8_t* src = latent + (size_t)i0 * lat_px * 96;
-    uint8_t* dst = rgb + (size_t)i0 * img_px * 3;
-    float* pre = prequant ? prequant + (size_t)i0 * img_px * 3 : nullptr;
-    if (host) {
-      const int s2 = idx & 1;
-      if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));
-      CK(h, cudaMemcpyAsync(d_lat[s2], src, nb * lat_px * 96, cudaMemcpyHostToDevice, h->h2d_stream));
-      CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
-      CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
-      if (int rc = decode_batch(h, d_lat[s2], nullptr, nb, lh, lw, d_rgb[s2], d_pre[s2], nullptr, st)) return rc;
-      CK(h, cudaEventRecord(h->ev_comp[s2], st));
-      CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
-      CK(h, cudaMemcpyAsync(dst, d_rgb[s2], nb * img_px * 3, cudaMemcpyDeviceToHost, h->d2h_stream));
-      if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * img_px * 3 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
-      CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
-    } else {
-      if (int rc = decode_batch(h, src, nullptr, nb, lh, lw, dst, pre, nullptr, st)) return rc;
+  auto run = [&]() -> int {
+    int idx = 0;
+    for (int i0 = 0; i0 < N; i0 += mb, ++idx) {
+      const int nb = (N - i0) < mb ? (N - i0) : mb;
+      const uint8_t* src = latent + (size_t)i0 * lat_px * 96;
+      uint8_t* dst = rgb + (size_t)i0 * img_px * 3;
+      float* pre = prequant ? prequant + (size_t)i0 * img_px * 3 : nullptr;
+      if (host) {
+        const int s2 = idx & 1;
+        if (idx >= 2) CK(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_out[s2], 0));
+        CK(h, cudaMemcpyAsync(d_lat[s2], src, nb * lat_px * 96, cudaMemcpyHostToDevice, h->h2d_stream));
+        CK(h, cudaEventRecord(h->ev_in[s2], h->h2d_stream));
+        CK(h, cudaStreamWaitEvent(st, h->ev_in[s2], 0));
+        if (int rc = decode_batch(h, d_lat[s2], nullptr, nb, lh, lw, d_rgb[s2], d_pre[s2], nullptr, st)) return rc;
+        CK(h, cudaEventRecord(h->ev_comp[s2], st));
+        CK(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[s2], 0));
+        CK(h, cudaMemcpyAsync(dst, d_rgb[s2], nb * img_px * 3, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (pre) CK(h, cudaMemcpyAsync(pre, d_pre[s2], nb * img_px * 3 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CK(h, cudaEventRecord(h->ev_out[s2], h->d2h_stream));
+      } else {
+        if (int rc = decode_batch(h, src, nullptr, nb, lh, lw, dst, pre, nullptr, st)) return rc;
+      }
     }
+    return 0;
+  };
+  if (int rc = run()) {
+    if (host) drain_streams(h, st);             // no copy into / out of the caller's buffers is left in flight
+    return rc;
   }
   if (host) { CK(h, cudaStreamSynchronize(h->d2h_stream)); CK(h, cudaStreamSynchronize(st)); if (int rc = check_device_error(h)) return rc; }
   return NNIC_OK;
@@ -999,6 +1076,7 @@ int nnic_run_encoder_planes(nnic_t* h, const float* planes, int N, int H, int W,
   if (N <= 0 || H <= 0 || W <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
   DeviceGuard g(h->device);
   if (int rc = check_device_ptrs(h, mem_kind, {{"planes", planes}, {"out", out}})) return rc;
+  if (int rc = check_device_error(h)) return rc;
   if (int rc = finalize_weights(h, 0)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -1030,6 +1108,7 @@ int nnic_run_decoder_planes(nnic_t* h, const float* planes, int N, int lh, int l
   if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "non-positive shape");
   DeviceGuard g(h->device);
   if (int rc = check_device_ptrs(h, mem_kind, {{"planes", planes}, {"out", out}})) return rc;
+  if (int rc = check_device_error(h)) return rc;
   if (int rc = finalize_weights(h, 1)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
@@ -1119,7 +1198,7 @@ int nnic_rate(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, int H, in
     CK(h, cudaMemcpyAsync(rb.d_lat, latent, lat_bytes, cudaMemcpyHostToDevice, st));
     d_lat = rb.d_lat;
   }
-  CKL(h, K_HIST, st, launch_hist(d_lat, N, (size_t)lh * lw, rb.d_hist, st));
+  CKL(h, K_HIST, st, launch_hist(d_lat, N, (size_t)lh * lw, rb.d_hist, h->num_sms, h->hist_variant, st));
   return rate_finish(h, N, lh, lw, H, W, hist, entropy_bits, bpp, hist_global, host, st, rb);
 }
 
@@ -1137,6 +1216,30 @@ int nnic_encode_rate(nnic_t* h, const uint8_t* rgb, int N, int H, int W, uint8_t
   if (int rc = rate_setup(h, N, 0, hist, entropy_bits, bpp, hist_global, host, st, rb)) return rc;
   if (int rc = encode_impl(h, rgb, N, H, W, latent, nullptr, rb.d_hist, mem_kind, stream)) return rc;
   return rate_finish(h, N, (H + 7) / 8, (W + 7) / 8, H, W, hist, entropy_bits, bpp, hist_global, host, st, rb);
+}
+
+int nnic_rate_channels(nnic_t* h, const uint8_t* latent, int N, int lh, int lw, uint64_t* hist_channels, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!latent || !hist_channels) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_rate_channels: NULL buffer");
+  if (N <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_rate_channels: non-positive shape");
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"latent", latent}, {"hist_channels", hist_channels}})) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pixels = (size_t)N * lh * lw, tab = (size_t)96 * 256 * 8;
+  if (mem_kind == NNIC_MEM_DEVICE) {
+    CKL(h, K_HIST, st, launch_hist_channels(latent, pixels, (unsigned long long*)hist_channels, h->num_sms, st));
+    return NNIC_OK;
+  }
+  if (int rc = ensure_buf(h, h->rate_scratch, pad1k(tab) + pad1k(pixels * 96) + 4096)) return rc;
+  unsigned long long* d_tab = (unsigned long long*)h->rate_scratch.ptr;
+  uint8_t* d_lat = (uint8_t*)h->rate_scratch.ptr + pad1k(tab);
+  CK(h, cudaMemcpyAsync(d_tab, hist_channels, tab, cudaMemcpyHostToDevice, st));
+  CK(h, cudaMemcpyAsync(d_lat, latent, pixels * 96, cudaMemcpyHostToDevice, st));
+  CKL(h, K_HIST, st, launch_hist_channels(d_lat, pixels, d_tab, h->num_sms, st));
+  CK(h, cudaMemcpyAsync(hist_channels, d_tab, tab, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  return NNIC_OK;
 }
 
 int nnic_hist_allreduce(nnic_t* h, void* nccl_comm, uint64_t* hist_global, void* stream) {

@@ -536,70 +536,169 @@ cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t*
 // (the reference builds them with 256 equal/reduce_sum passes), p = count/numel,
 // H = sum p * (-log(clip(p,1e-5,1)) / log 2).
 //
-// One block works on a contiguous chunk of one image.  Each warp owns a private [3][256] u32
-// histogram in shared memory; symbols 0 (about half of a typical latent) never touch the atomics:
-// they are counted with a ballot/popc per plane.
-constexpr int HIST_WARPS = 8;
+// One block works on block-strided chunks of ONE image and keeps NC interleaved copies of its [3][256] u32 table in
+// shared memory: counter (plane, bin) of copy c sits at word (plane*256 + bin)*NC + c, and lane l of every warp uses copy
+// l % NC.  Shared-memory atomics serialise lanes of one instruction that hit the same ADDRESS or the same BANK; with the
+// copies interleaved, lanes that count the same symbol (a typical latent has ~50 distinct symbols, so many lanes do) land in
+// different banks, and two lanes collide only when they share a copy (32/NC lanes) and their bins differ by a multiple of
+// 32/NC.  Symbols 0 (about half of a typical latent) never touch the atomics: they are counted by subtraction.  Round 1's
+// per-warp tables (all 32 lanes in one copy) ran at 1.65 TB/s on the 805 MB latent of config 5; see DESIGN.md section 5
+// and profiles/r2_hist_variants.log for the copies / occupancy sweep.
+constexpr int HIST_THREADS = 256;
 constexpr int HIST_CHUNK = 96 * 256;          // bytes per block-iteration: a multiple of 96 and of 16*256
 
-__global__ void __launch_bounds__(HIST_WARPS * 32) k_hist(const uint8_t* __restrict__ latent,
-                                                          size_t bytes_per_image, int chunks_per_image,
-                                                          uint32_t* __restrict__ hist) {
-  __shared__ uint32_t h_s[HIST_WARPS][3][256];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < HIST_WARPS * 3 * 256; i += HIST_WARPS * 32) (&h_s[0][0][0])[i] = 0;
+template <int NC>
+__global__ void __launch_bounds__(HIST_THREADS) k_hist(const uint8_t* __restrict__ latent, size_t bytes_per_image,
+                                                        int chunks_per_image, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t h_s[];              // [3][256][NC]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 3 * 256 * NC; i += HIST_THREADS) h_s[i] = 0;
   __syncthreads();
   const int n = blockIdx.x / chunks_per_image, chunk = blockIdx.x - n * chunks_per_image;
   const uint8_t* base = latent + (size_t)n * bytes_per_image;
-  uint32_t zeros[3] = {0, 0, 0};
-  // block-stride over the image in HIST_CHUNK pieces; thread t of a piece reads bytes [16t, 16t+16)
+  uint32_t* my = h_s + (lane & (NC - 1));
+  uint32_t block_bytes = 0;                      // bytes of the image this block has covered (the same in every thread)
+  // block-stride over the image in HIST_CHUNK pieces; thread t of a piece reads bytes [16t, 16t+16), 6 loads in flight
   for (size_t off = (size_t)chunk * HIST_CHUNK; off < bytes_per_image; off += (size_t)chunks_per_image * HIST_CHUNK) {
+    constexpr int LOADS = HIST_CHUNK / (16 * HIST_THREADS);
+    uint4 raw[LOADS];
+    bool ok[LOADS];
 #pragma unroll
-    for (int it = 0; it < HIST_CHUNK / (16 * HIST_WARPS * 32); ++it) {
-      const size_t o = off + ((size_t)it * HIST_WARPS * 32 + tid) * 16;
-      const bool ok = o < bytes_per_image;        // bytes_per_image is a multiple of 96, hence of 16
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (ok) raw = *reinterpret_cast<const uint4*>(base + o);
+    for (int it = 0; it < LOADS; ++it) {
+      const size_t o = off + ((size_t)it * HIST_THREADS + tid) * 16;
+      ok[it] = o < bytes_per_image;              // bytes_per_image is a multiple of 96, hence of 16
+      raw[it] = ok[it] ? __ldg(reinterpret_cast<const uint4*>(base + o)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int it = 0; it < LOADS; ++it) {
+      const size_t o = off + ((size_t)it * HIST_THREADS + tid) * 16;
       // 16 bytes never straddle a 32-channel plane group: o % 96 in {0,16,...,80}
       const int plane = (int)((o % 96) >> 5);
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-      uint32_t nz = 0;
+      uint32_t* tab = my + plane * 256 * NC;
+      const uint32_t w[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const uint32_t s = (w[k] >> (8 * b)) & 0xffu;
-          if (ok && s != 0) atomicAdd(&h_s[warp][plane][s], 1u);
-          nz += (s != 0);
+          const uint32_t sy = (w[k] >> (8 * b)) & 0xffu;
+          if (sy != 0) atomicAdd(tab + sy * NC, 1u);       // padded lanes (ok == false) hold zeros
         }
       }
-      if (ok) zeros[plane] += 16 - nz;
     }
+    const size_t left = bytes_per_image - off;
+    block_bytes += (uint32_t)(left < (size_t)HIST_CHUNK ? left : (size_t)HIST_CHUNK);
   }
+  // zeros of a plane = symbols seen - non-zero symbols counted.  Every piece is a whole number of 96-byte pixels, so each
+  // plane has seen exactly a third of the block's bytes.
+  const uint32_t seen_per_plane = block_bytes / 3;
+  // thread t sums the copies of bins t, t + 256, t + 512 (one per plane); bin 0 = seen - sum of the others
+  __shared__ uint32_t nz_s[3];
+  if (tid < 3) nz_s[tid] = 0;
+  __syncthreads();
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
-    uint32_t z = zeros[p];
+    uint32_t sum = 0;
+    const uint32_t* row = h_s + (p * 256 + tid) * NC;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) z += __shfl_xor_sync(0xffffffffu, z, d);
-    if (lane == 0 && z) atomicAdd(&h_s[warp][p][0], z);
+    for (int c = 0; c < NC; ++c) sum += row[(c + tid) & (NC - 1)];      // staggered start: the 32 lanes read 32 banks
+    if (tid != 0 && sum) atomicAdd(&hist[(size_t)n * 768 + p * 256 + tid], sum);
+    uint32_t t = tid != 0 ? sum : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (lane == 0 && t) atomicAdd(&nz_s[p], t);
   }
   __syncthreads();
-  for (int i = tid; i < 3 * 256; i += HIST_WARPS * 32) {
-    uint32_t s = 0;
-#pragma unroll
-    for (int w = 0; w < HIST_WARPS; ++w) s += (&h_s[w][0][0])[i];
-    if (s) atomicAdd(&hist[(size_t)n * 768 + i], s);
+  if (tid < 3 && seen_per_plane > nz_s[tid]) atomicAdd(&hist[(size_t)n * 768 + tid * 256], seen_per_plane - nz_s[tid]);
+}
+
+template <int NC>
+static cudaError_t launch_hist_nc(const uint8_t* latent, int N, size_t bytes, int num_sms, int blocks_per_sm, uint32_t* hist,
+                                  cudaStream_t stream) {
+  static unsigned long long attr_devices = 0;
+  constexpr int SMEM = 3 * 256 * NC * 4;
+  if (first_use_on_device(attr_devices)) {
+    cudaError_t e = cudaFuncSetAttribute(k_hist<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+  }
+  // enough blocks to fill the machine (blocks_per_sm resident per SM), at most one per chunk
+  const size_t chunks_total = (bytes + HIST_CHUNK - 1) / HIST_CHUNK;
+  const size_t want = ((size_t)num_sms * blocks_per_sm + N - 1) / N;
+  int chunks_per_image = (int)(chunks_total < want ? chunks_total : want);
+  if (chunks_per_image < 1) chunks_per_image = 1;
+  k_hist<NC><<<(unsigned)((size_t)N * chunks_per_image), HIST_THREADS, SMEM, stream>>>(latent, bytes, chunks_per_image, hist);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, int num_sms, int variant,
+                        cudaStream_t stream) {
+  const size_t bytes = pixels_per_image * 96;
+  // variant (development, NNIC_HIST_VARIANT): copies * 100 + resident blocks per SM; default 16 copies (48 KB), 4 blocks
+  const int nc = variant > 0 ? variant / 100 : 16, bps = variant > 0 ? variant % 100 : 4;
+  switch (nc) {
+    case 1: return launch_hist_nc<1>(latent, N, bytes, num_sms, bps, hist, stream);
+    case 4: return launch_hist_nc<4>(latent, N, bytes, num_sms, bps, hist, stream);
+    case 8: return launch_hist_nc<8>(latent, N, bytes, num_sms, bps, hist, stream);
+    case 32: return launch_hist_nc<32>(latent, N, bytes, num_sms, bps, hist, stream);
+    default: return launch_hist_nc<16>(latent, N, bytes, num_sms, bps, hist, stream);
   }
 }
 
-cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, cudaStream_t stream) {
-  const size_t bytes = pixels_per_image * 96;
-  // enough blocks to fill the machine a few times over, at most one per chunk
-  size_t chunks_total = (bytes + HIST_CHUNK - 1) / HIST_CHUNK;
-  size_t want = (size_t)(148 * 8 + N - 1) / N;
-  int chunks_per_image = (int)(chunks_total < want ? chunks_total : want);
-  if (chunks_per_image < 1) chunks_per_image = 1;
-  k_hist<<<(unsigned)(N * chunks_per_image), HIST_WARPS * 32, 0, stream>>>(latent, bytes, chunks_per_image, hist);
+// Per latent FEATURE CHANNEL counts [96][256], summed over the whole batch (the finer table BASELINE.json's "per-channel
+// latent histogram" names; the reference's own histogram, tf1_13/src/training.py:62-68, is the per-plane one above, and the
+// 32 rows of a plane add up to it).  One block owns a [96][256] u32 table in shared memory (96 KB) and walks pixels
+// block-strided; a thread reads 16 channels of one pixel.  Zero symbols (about half of a latent) skip the atomics: every
+// channel sees every pixel once, so count[c][0] = pixels - sum_{s>0} count[c][s] at flush time.
+constexpr int HCH_THREADS = 384;              // 6 threads per pixel (96 channels / 16), 64 pixels per block-iteration
+
+__global__ void __launch_bounds__(HCH_THREADS) k_hist_channels(const uint8_t* __restrict__ latent, size_t total_pixels,
+                                                                unsigned long long* __restrict__ hist_ch) {
+  extern __shared__ uint32_t hc_s[];           // [96][256]
+  for (int i = threadIdx.x; i < 96 * 256; i += HCH_THREADS) hc_s[i] = 0;
+  __syncthreads();
+  const int sub = threadIdx.x % 6, pix_in_iter = threadIdx.x / 6;
+  size_t my_pixels = 0;
+  for (size_t p0 = (size_t)blockIdx.x * 64; p0 < total_pixels; p0 += (size_t)gridDim.x * 64) {
+    const size_t px = p0 + pix_in_iter;
+    if (px < total_pixels) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(latent + px * 96 + sub * 16);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t sym = (w[k] >> (8 * b)) & 0xffu;
+          if (sym) atomicAdd(&hc_s[(sub * 16 + k * 4 + b) * 256 + sym], 1u);
+        }
+      }
+    }
+    const size_t left = total_pixels - p0;
+    my_pixels += left < 64 ? left : 64;         // identical in every thread: pixels this block has covered
+  }
+  __syncthreads();
+  // flush: bin 0 of a channel is derived from the pixel count (one thread per channel; once per block)
+  for (int c = threadIdx.x; c < 96; c += HCH_THREADS) {
+    unsigned long long nz = 0;
+    for (int sbin = 1; sbin < 256; ++sbin) nz += hc_s[c * 256 + sbin];
+    if (my_pixels > nz) atomicAdd(&hist_ch[c * 256], (unsigned long long)my_pixels - nz);
+  }
+  for (int i = threadIdx.x; i < 96 * 256; i += HCH_THREADS) {
+    const uint32_t v = hc_s[i];
+    if ((i & 255) && v) atomicAdd(&hist_ch[i], (unsigned long long)v);
+  }
+}
+
+cudaError_t launch_hist_channels(const uint8_t* latent, size_t total_pixels, unsigned long long* hist_ch, int num_sms,
+                                 cudaStream_t stream) {
+  static unsigned long long attr_devices = 0;
+  constexpr int SMEM = 96 * 256 * 4;
+  if (first_use_on_device(attr_devices)) {
+    cudaError_t e = cudaFuncSetAttribute(k_hist_channels, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+  }
+  size_t want = (total_pixels + 63) / 64;
+  const size_t cap = (size_t)num_sms * 2;       // two 96 KB tables per SM
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+  k_hist_channels<<<grid, HCH_THREADS, SMEM, stream>>>(latent, total_pixels, hist_ch);
   return cudaGetLastError();
 }
 
@@ -617,20 +716,26 @@ cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* 
   return cudaGetLastError();
 }
 
-// one block of 256 threads per histogram row (one thread per bin)
+// One block of 256 threads per histogram row (one thread per bin).
+// tf1_13/src/training.py:69-70: p_i = count_i / numel, H = sum_i p_i * (-log(clip(p_i, 1e-5, 1)) / log 2).
+// numel is the exact integer sum of the counts (u64 warp/block reduction: the all-rank counts of config 5 are ~2e9 per
+// plane, far beyond the 2^24 a float can count).  p_i is the correctly rounded fp32 quotient of the two exact integers
+// (computed in double, then rounded once), which is what the reference's fp32 division gives whenever its operands are
+// exact (count, numel < 2^24) and the defined value beyond that.  The rest follows the reference's fp32 op order.
 template <typename CountT>
 __device__ __forceinline__ float entropy_row(const CountT* __restrict__ row, float* red) {
-  const int tid = threadIdx.x;
-  const float c = (float)row[tid];
-  red[tid] = c;
+  __shared__ unsigned long long tot_s[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long c = (unsigned long long)row[tid];
+  unsigned long long t = c;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0) tot_s[warp] = t;
   __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (tid < d) red[tid] += red[tid + d];   // counts are integers: exact below 2^24 per partial sum
-    __syncthreads();
-  }
-  const float numel = red[0];
-  __syncthreads();
-  const float p = numel > 0.0f ? __fdiv_rn(c, numel) : 0.0f;
+  unsigned long long numel = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) numel += tot_s[w];
+  const float p = numel > 0 ? (float)((double)c / (double)numel) : 0.0f;
   const float pc = fminf(fmaxf(p, 1e-5f), 1.0f);
   const float term = __fmul_rn(p, __fdiv_rn(-logf(pc), logf(2.0f)));
   red[tid] = term;

@@ -6,7 +6,14 @@ namespace nnic {
 namespace tc {
 
 constexpr int kTileRows = 16, kTileCols = 8, kTileM = 128;
-constexpr uint64_t kWaitTimeoutCycles = 4000000000ull;   // ~2 s: a hung barrier traps instead of hanging the GPU
+// Bounded barrier waits: a wait that lasts longer than `timeout` SM cycles writes `code` to the handle's mapped host flag and
+// traps (a hung barrier must not hang the GPU box).  The bound is per handle (NNIC_TC_TIMEOUT_MS at nnic_create, default
+// 2000 ms at 2 GHz); 0 disables it -- for runs under ncu replay, cuda-gdb, MPS or time-slicing, where a wait can last
+// arbitrarily long without being hung.
+struct WaitCtx {
+  int* error_flag;
+  unsigned long long timeout;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -42,13 +49,13 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const WaitCtx& wc, int code) {
   if (mbar_test(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if ((unsigned long long)clock64() - t0 > kWaitTimeoutCycles) {
-      if (error_flag) atomicExch(error_flag, code);
+    if (wc.timeout && (unsigned long long)clock64() - t0 > wc.timeout) {
+      if (wc.error_flag) atomicExch(wc.error_flag, code);
       __threadfence_system();
       __trap();
     }

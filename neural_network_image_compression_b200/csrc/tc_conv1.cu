@@ -78,6 +78,7 @@ template <int IN_KIND /*0 rgb u8, 1 f32 planes*/>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, int num_tiles, int* error_flag) {
   extern __shared__ uint8_t smem_raw[];
+  const WaitCtx wc{error_flag, prm.wait_timeout};
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + W_OFF;
@@ -196,7 +197,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       }
       it.next(tiles_x, tiles_y);
       if (it.p < P) load_raw(it);                // next tile of this group
-      mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);      // the MMAs that read this stage are done
+      mbar_wait(&empty_bar[stage], phase ^ 1, wc, 1);      // the MMAs that read this stage are done
       group_barrier(g);
       // K column k = kh*5 + kw for k < 25, zero above; each thread builds the rows of two pixels
       uint8_t* a_hi = stage_base + stage * STAGE_BYTES;
@@ -225,7 +226,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       group_barrier(g);                          // both warps of the group have written their rows
       if ((warp & (kBuilderWarps / GROUPS - 1)) == 0) {
         // ---- MMA issue: A_hi x [W_hi | W_lo] and A_lo x W_hi, two k-steps, into TMEM slot `stage`
-        mbar_wait(&slot_empty[stage], phase ^ 1, error_flag, 2);
+        mbar_wait(&slot_empty[stage], phase ^ 1, wc, 2);
         tc_fence_after();
         if (elect_one()) {
           const int set = p < N ? 0 : 1;
@@ -258,7 +259,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     int slot = 0; uint32_t slot_phase = 0;
     uint32_t am[HALF], ac[HALF], bm[HALF], bc[HALF];
     auto issue_loads = [&](uint32_t* vm, uint32_t* vc) {
-      mbar_wait(&slot_full[slot], slot_phase, error_flag, 4);
+      mbar_wait(&slot_full[slot], slot_phase, wc, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
       tmem_ld16_nowait(taddr, vm);

@@ -84,6 +84,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
   using C = PCfg<RB, NSPLIT, COUT>;
+  const WaitCtx wc{error_flag, prm.wait_timeout};
   constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
                 BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
@@ -140,10 +141,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const int txy = it % tiles_per_plane, p = it / tiles_per_plane;
       const int Y0 = (txy / tiles_x) * kTileRows, X0 = (txy % tiles_x) * kTileCols;
       for (int q = 0; q < prm.npatch; ++q) {
-        mbar_wait(&patch_empty[pb], pphase ^ 1, error_flag, 1);
+        mbar_wait(&patch_empty[pb], pphase ^ 1, wc, 1);
         if (elect_one()) {
           uint8_t* pbuf = patch_base + pb * SET_BYTES;
-          if (prm.dbg & 16) {
+          if ((prm.dbg & 16) || ((prm.dbg & 64) && it >= (int)blockIdx.x + NSETS * (int)gridDim.x)) {   // 64: only the first NSETS items load
             mbar_arrive(&patch_full[pb]);
           } else {
             mbar_expect_tx(&patch_full[pb], FAST ? PATCH_TX : 2 * PATCH_TX);
@@ -158,6 +159,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else if (warp == 0) {
     // ===================== TMA producer: weight groups =====================
     int ws = 0; uint32_t wphase = 0;
+    int w_loaded = 0;
     long long tw_patch = 0, tw_w = 0, t_begin = TICK();
     for (int base = base0; base < num_items; base += gridDim.x) {
       const int it = base + crank, it_peer = base + (crank ^ 1);
@@ -176,10 +178,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
         const int send = nseg == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
         for (int s0 = sbeg; s0 < send; ++s0, ++tap) {          // one weight tile per tap, in the order the issuers consume them
-          { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, error_flag, 2); tw_w += TICK() - t0; }
+          { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, wc, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
             uint8_t* wb = w_base + ws * W_SLOT;
-            if (prm.dbg & 4) {
+            if ((prm.dbg & 4) || ((prm.dbg & 32) && w_loaded >= WSLOTS)) {   // 32: only the first ring pass loads (real data, no refills)
               mbar_arrive(&w_full[ws]);
             } else {
               mbar_expect_tx(&w_full[ws], FAST ? W_TILE : W_SLOT);
@@ -195,6 +197,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
           }
           __syncwarp();
+          ++w_loaded;
           if (++ws == WSLOTS) { ws = 0; wphase ^= 1; }
         }
       }
@@ -215,7 +218,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     for (int base = base0; base < num_items; base += gridDim.x) {
       const bool active = base + crank < num_items;
       for (int seg = 0; seg < prm.npatch; ++seg) {
-      if (active) { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, error_flag, 3); tw_patch += TICK() - t0; }
+      if (active) { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, wc, 3); tw_patch += TICK() - t0; }
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
       const int njobs_seg = prm.npatch == 1 ? prm.njobs : 1;
       for (int j = 0; j < njobs_seg; ++j) {
@@ -232,7 +235,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           uint32_t a_off[GTAPS];
 #pragma unroll
           for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
-          if (active) { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 4); tw_slot += TICK() - t0; }
+          if (active) { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 4); tw_slot += TICK() - t0; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
           const long long ti0 = TICK();
@@ -242,7 +245,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int k = 0; k < GTAPS; ++k) {
               if (k < ntaps) {
-                { long long t1 = TICK(); mbar_wait(&w_full[w], wp, error_flag, 5); tw_w += TICK() - t1; }
+                { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
                 tc_fence_after();
                 if (active && !(prm.dbg & 1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
@@ -325,7 +328,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         for (int ch = 0; ch < nchains; ++ch) {
           long long te0 = TICK();
-          mbar_wait(&slot_full[slot], slot_phase, error_flag, 6);
+          mbar_wait(&slot_full[slot], slot_phase, wc, 6);
           long long te1 = TICK(); tw_full += te1 - te0;
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;

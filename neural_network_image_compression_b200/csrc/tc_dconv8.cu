@@ -50,6 +50,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
             const __grid_constant__ TcDconv8Params prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
   extern __shared__ uint8_t smem_raw[];
+  const WaitCtx wc{error_flag, prm.wait_timeout};
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + W_OFF;                               // [set][W_hi | W_lo]
@@ -99,7 +100,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int txy = it % tiles_per_image, n = it / tiles_per_image;
       const int Y0 = (txy / tiles_x) * IH - 1, X0 = (txy % tiles_x) * IW - 1;
       for (int plane = 0; plane < 3; ++plane) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, error_flag, 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1, wc, 1);
         if (elect_one()) {
           uint8_t* sb = stage_base + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], prm.fast ? A_BYTES : STAGE_BYTES);
@@ -115,13 +116,13 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     constexpr uint32_t idesc_wide = make_idesc(2 * NT);
     constexpr uint32_t idesc_narrow = make_idesc(NT);
     const uint32_t stage_u32 = smem_u32(stage_base), w_u32 = smem_u32(w_base);
-    mbar_wait(w_bar, 0, error_flag, 2);
+    mbar_wait(w_bar, 0, wc, 2);
     int stage = 0; uint32_t phase = 0;
     int slot = 0; uint32_t slot_phase = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       for (int plane = 0; plane < 3; ++plane) {
-        mbar_wait(&slot_empty[slot], slot_phase ^ 1, error_flag, 3);
-        mbar_wait(&full_bar[stage], phase, error_flag, 4);
+        mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 3);
+        mbar_wait(&full_bar[stage], phase, wc, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
         const uint64_t a_hi = make_smem_desc<128>(stage_u32 + stage * STAGE_BYTES);
@@ -167,7 +168,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const int cnt = 3 * k_item + plane;
         const int slot = cnt & (SLOTS - 1);
         const uint32_t slot_phase = (cnt / SLOTS) & 1;
-        mbar_wait(&slot_full[slot], slot_phase, error_flag, 5);
+        mbar_wait(&slot_full[slot], slot_phase, wc, 5);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS;
         uint32_t vm[NT], vc[NT];

@@ -55,7 +55,7 @@ class Encoder(ProClass):
         """Encoder.__call__ plus the histogram/entropy rate of tf1_13/src/training.py:62-71 in one pass: the
         symbols are counted by the kernel that quantises them (nnic_encode_rate), the latent is not read again.
         Returns (latent, Rate); identical to `lat = enc(x); r = rate(enc.handle, lat, H, W)`."""
-        from .rate import Rate
+        from .rate import Rate, check_count_table
         lib, h = self.handle.lib, self.handle.h
         if _is_torch(x):
             import torch
@@ -75,6 +75,8 @@ class Encoder(ProClass):
             bpp = torch.empty((n,), dtype=torch.float32, device=dev)
             if hist_global is None:
                 hist_global = torch.zeros((3, 256), dtype=torch.int64, device=dev)
+            else:
+                hist_global = check_count_table(hist_global, (3, 256), True, self.device)
             self.handle.check(lib.nnic_encode_rate(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(hist), _ptr(ent), _ptr(bpp),
                                                    _ptr(hist_global), MEM_DEVICE, _stream_of(x)), "nnic_encode_rate")
             return out, Rate(hist, ent, bpp, hist_global)
@@ -92,6 +94,8 @@ class Encoder(ProClass):
         bpp = np.empty((n,), np.float32)
         if hist_global is None:
             hist_global = np.zeros((3, 256), np.uint64)
+        else:
+            hist_global = check_count_table(hist_global, (3, 256), False, self.device)
         self.handle.check(lib.nnic_encode_rate(h, _ptr(x), n, hh, ww, _ptr(out), _ptr(hist), _ptr(ent), _ptr(bpp),
                                                _ptr(hist_global), MEM_HOST, None), "nnic_encode_rate")
         return out, Rate(hist, ent, bpp, hist_global)

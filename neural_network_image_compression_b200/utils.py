@@ -17,11 +17,6 @@ from .container import DatasetDriver, read_dataset, save_img  # noqa: F401  (uti
 
 _MODELS = list(W.MODEL_SUFFIXES)
 
-# tf2_0/src/utils.py:7-9 (kept for callers that import them; the kernels use their fp32 roundings)
-ycbcr_kernel = np.array([[0.299, 0.587, 0.114], [-0.16874, -0.33126, 0.5], [0.5, -0.41869, -0.08131]])
-ycbcr_inv_kernel = np.linalg.inv(ycbcr_kernel)
-ycbcr_off = np.array([0, 0.5, 0.5])
-
 
 def _is_torch(x) -> bool:
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
@@ -52,11 +47,15 @@ class ProClass(DatasetDriver):
         self.weights[model_index] = w
 
     def init_random(self, seeds=None, gain: float = 1.0, bias_range: float = 0.0):
-        """Keras-default initialisation (what a freshly constructed reference model holds)."""
+        """Keras-default initialisation (what a freshly constructed reference model holds), drawn by the library itself
+        (nnic_init_random_scaled: NumPy's default_rng stream, so the networks equal weights.glorot_uniform(kind, seed));
+        `self.weights` keeps the same arrays for save() and for the parity tests."""
         prefix = "enc" if self.kind == "encoder" else "dec"
         for i, name in enumerate(_MODELS):
             seed = (seeds or W.DEFAULT_SEEDS)[prefix + name] if not isinstance(seeds, (list, tuple)) else seeds[i]
-            self.set_weights(i, W.glorot_uniform(self.kind, seed, gain, bias_range))
+            self.handle.check(self.handle.lib.nnic_init_random_scaled(self.handle.h, self._set_base + i, int(seed), float(gain),
+                                                                      float(bias_range)), "nnic_init_random_scaled")
+            self.weights[i] = W.glorot_uniform_native(self.kind, seed, gain, bias_range)
         return self
 
     def load(self, path: str):

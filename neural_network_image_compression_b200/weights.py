@@ -52,6 +52,30 @@ def glorot_uniform(kind: str, seed: int, gain: float = 1.0, bias_range: float = 
     return out
 
 
+def glorot_uniform_native(kind: str, seed: int, gain: float = 1.0, bias_range: float = 0.0, set_index: int | None = None) -> dict:
+    """The same network drawn by libnnic.so (nnic_glorot_uniform: PCG64 / SeedSequence restated in C++; host code, no
+    GPU needed).  Bit-identical to glorot_uniform() -- tests/test_host.py::test_c_glorot_matches_numpy."""
+    from ._lib import load_library
+    lib = load_library()
+    if set_index is None:
+        set_index = SET_ENC_Y if kind == "encoder" else SET_DEC_Y
+    layers = layers_of(kind)
+    nk = sum(k * k * cin * cout for _n, k, _s, cin, cout in layers)
+    nb = sum(cout for *_r, cout in layers)
+    kern, bias = np.empty(nk, np.float32), np.empty(nb, np.float32)
+    rc = lib.nnic_glorot_uniform(int(set_index), int(seed), float(gain), float(bias_range), kern.ctypes.data, bias.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"nnic_glorot_uniform failed ({rc})")
+    out, ko, bo = {}, 0, 0
+    for name, k, _s, cin, cout in layers:
+        n = k * k * cin * cout
+        out[name + "/kernel"] = kern[ko:ko + n].reshape(kernel_shape(kind, k, cin, cout)).copy()
+        out[name + "/bias"] = bias[bo:bo + cout].copy()
+        ko += n
+        bo += cout
+    return out
+
+
 def check_weight_set(kind: str, w: dict) -> None:
     for name, k, _s, cin, cout in layers_of(kind):
         kern, bias = w[name + "/kernel"], w[name + "/bias"]

@@ -258,3 +258,27 @@ def test_c_example_compiles_as_pedantic_c99(tmp_path):
                         os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", lib_dir, "-lnnic", f"-Wl,-rpath,{lib_dir}", "-lm",
                         "-o", str(tmp_path / "demo")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_c_glorot_matches_numpy():
+    """nnic_glorot_uniform / nnic_init_random (include/nnic.h) restate NumPy's default_rng(seed) stream in C++: the
+    networks a C caller gets are bit-identical to weights.glorot_uniform(kind, seed), i.e. to the oracle's weight sets.
+    Host code only: runs without a GPU."""
+    import ctypes as C
+    import neural_network_image_compression_b200 as nn
+    from neural_network_image_compression_b200 import weights as Wt
+    lib = nn.load_library()
+    for set_index, kind, seed, gain, br in ((0, "encoder", 11, 1.0, 0.0), (1, "encoder", 12, 1.6, 0.05),
+                                            (2, "decoder", 13, 1.0, 0.0), (3, "decoder", 14, 1.6, 0.05),
+                                            (0, "encoder", 0, 1.0, 0.0), (3, "decoder", (1 << 40) + 5, 0.5, 1.0)):
+        want = Wt.glorot_uniform(kind, seed, gain, br)
+        got = Wt.glorot_uniform_native(kind, seed, gain, br, set_index)
+        assert got.keys() == want.keys()
+        for k in want:
+            assert got[k].dtype == np.float32 and got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), (set_index, seed, k)
+    k, cin, cout = C.c_int(), C.c_int(), C.c_int()
+    for set_index, kind in ((0, "encoder"), (2, "decoder")):
+        for li, (_name, kk, _s, ci, co) in enumerate(Wt.layers_of(kind)):
+            assert lib.nnic_layer_shape(set_index, li, C.byref(k), C.byref(cin), C.byref(cout)) == 0
+            assert (k.value, cin.value, cout.value) == (kk, ci, co)
+    assert lib.nnic_layer_shape(4, 0, None, None, None) == -1 and lib.nnic_glorot_uniform(0, 1, 1.0, 0.0, None, None) == -1

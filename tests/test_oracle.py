@@ -140,3 +140,53 @@ def test_c_restatement_agrees_with_the_python_oracle():
             ra = CO.decode_prequant(sym, dY, dC)
             rb = O.decode_prequant(sym, dY, dC, "f64")
             assert ra.shape == rb.shape and np.abs(ra - rb).max() < 1e-12
+
+
+# ---- the full-size parity records (tests/parity_fixture.py) describe what the oracle computes today ----------------
+@pytest.mark.parametrize("config,wname,indices", [("c2", "spread", (0, 17)), ("c2", "default", (5,)),
+                                                  ("c3", "spread", (0, 1, 2047, 4095)), ("c3", "default", (7, 3000)),
+                                                  ("c5", "spread", (0, 2047)), ("c5", "default", (1024,))])
+def test_parity_records_against_live_oracle(config, wname, indices):
+    """Sampled images of every full-size record are recomputed with the live oracle (fp64 and fp32): same digest of the
+    bytes outside the tie band, same tie positions and tie bytes.  (Config 4's 4K images take minutes per image in fp64;
+    its record is produced by the same code path, tools/make_parity_fixtures.py::make.)"""
+    import parity_fixture as PF
+    rec = PF.load_record(f"parity_{config}_{wname}")
+    eY, eC, dY, dC = make_weights(wname)
+    if config == "c2":
+        images = PF.c2_images()
+    elif config == "c3":
+        images = PF.c3_patches()
+    else:
+        images = np.concatenate([PF.c5_patches(i, 1).numpy() for i in indices])
+    assert tuple(rec["shape"][1:]) == images.shape[1:]
+    img = images[list(indices)] if config != "c5" else images
+    pre64 = O.encode_prequant(img, eY, eC, "f64")
+    PF.verify_images_with_live_oracle(rec, "lat", indices, pre64 * 255.0, O.encode(img, eY, eC, "f32"))
+    if config == "c2":
+        sym64 = O.quantise(pre64)
+        d64 = O.decode_prequant(sym64, dY, dC, "f64")
+        PF.verify_images_with_live_oracle(rec, "rec", indices, d64 * 255.0, O.decode(sym64, dY, dC, "f32"))
+
+
+def test_parity_record_compare_detects_a_wrong_byte():
+    """compare() must reject one flipped byte outside the tie band and a tie byte that is neither floor nor floor + 1."""
+    import parity_fixture as PF
+    rec = PF.load_record("parity_c2_spread")
+    eY, eC, _dY, _dC = make_weights("spread")
+    img = PF.c2_images()[:1]
+    sym = O.encode(img, eY, eC, "f64")
+    st = PF.compare(sym, rec, "lat", first_image=0)
+    assert st["mismatch_vs_f64"] == 0 and st["mismatch_outside_tie_band"] == 0
+    ties = set(PF.tie_positions(rec, "lat")[:100000].tolist())
+    k = next(i for i in range(sym.size) if i not in ties)
+    bad = sym.copy(); bad.reshape(-1)[k] ^= 1
+    with pytest.raises(AssertionError, match="outside the rounding-tie band"):
+        PF.compare(bad, rec, "lat", first_image=0)
+    t = int(PF.tie_positions(rec, "lat")[0])
+    bad = sym.copy(); bad.reshape(-1)[t] = (int(rec["lat_tie_floor"][0]) + 2) & 0xff
+    with pytest.raises(AssertionError, match="neither floor nor floor"):
+        PF.compare(bad, rec, "lat", first_image=0)
+    # a legal tie flip is counted, not rejected
+    ok = sym.copy(); f = int(rec["lat_tie_floor"][0]); ok.reshape(-1)[t] = f + 1 if int(sym.reshape(-1)[t]) == f else f
+    assert PF.compare(ok, rec, "lat", first_image=0)["mismatch_vs_f64"] == 1
