@@ -55,8 +55,9 @@ cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float*
                           float* planes, cudaStream_t stream);
 
 // ---- latent u8 [N,lh,lw,96] -> /255 -> planes [3N,lh,lw,32] (split fp16 or f32) -----------------
+// integer_symbols: out_hi receives the symbols themselves (0..255, exact in fp16) and out_lo is not written
 cudaError_t launch_latent_expand(const uint8_t* latent, int N, int lh, int lw, __half* out_hi,
-                                 __half* out_lo, float* out_f32, cudaStream_t stream);
+                                 __half* out_lo, float* out_f32, bool integer_symbols, cudaStream_t stream);
 // f32 -> split fp16, elementwise (count elements, multiple of 4)
 cudaError_t launch_f32_to_split(const float* in, size_t count, __half* out_hi, __half* out_lo,
                                 cudaStream_t stream);
@@ -108,6 +109,7 @@ struct TcPatchParams {
   int cout;                   // 64, or 32 (conv8)
   int fast;                   // one fp16 product per MAC, hi planes only (decoder, nnic_set_decode_precision)
   int cluster;                // 2: CTA pairs share every weight tile through TMA multicast; else 1
+  int a_hi_only;              // the input is exact in its hi plane (integer latent symbols): no lo plane, no A_lo x W_hi product
   unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded (tc_common.cuh WaitCtx)
   int P, n_split;
   int Hp, Wp;
@@ -124,7 +126,7 @@ struct TcPatchParams {
   float* out_prequant;        // TC_OUT_QUANT, optional: f32 [N,Ho,Wo,96]
   uint32_t* hist;             // TC_OUT_QUANT, optional: [N][3][256] symbol counts, added to (tf1_13/src/training.py:62-68)
   long long* dbg_buf;         // development: per-CTA role timers [grid][4][8] (NNIC_TC_PROF)
-  int dbg;                    // development switches (NNIC_TC_DBG): 1 skip MMAs, 2 skip stores, 4 skip W loads, 8 skip TMEM loads
+  int dbg;                    // development switches (NNIC_TC_DBG): 1 skip MMAs, 2 skip stores, 4 skip W loads, 8 skip TMEM loads, 16 skip patch loads, 32 / 64 load W / patches only once
   __half* out_hi;
   __half* out_lo;
   float* out_f32;

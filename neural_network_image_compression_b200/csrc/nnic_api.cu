@@ -77,6 +77,8 @@ struct nnic_handle {
   uint32_t* fused_hist = nullptr;   // set around conv8's launch by encode_batch: device [nb][3][256] counts to add to
   int tc_cluster = 0;               // weight tiles multicast to CTA pairs: NNIC_TC_CLUSTER=0 never, 1 residual layers, 2 all
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
+  bool int_latent = true;           // dconv1 multiplies the integer symbols and folds /255 into its epilogue (NNIC_INT_LATENT=0: x/255 split in two planes)
+  bool a_hi_only = false;           // set around dconv1's launch by decode_batch when its input is the integer symbol plane
   EncodeTiledFn encode_tiled = nullptr;
   unsigned long long wait_timeout = 4000000000ull;   // barrier-wait bound in SM cycles (NNIC_TC_TIMEOUT_MS, 0 = none)
   int hist_variant = 0;             // NNIC_HIST_VARIANT (development): copies * 100 + blocks per SM of k_hist
@@ -358,7 +360,7 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
     h->w_edge[net] = w;
     h->b_edge[net] = b;
     if (net == 0) {
-      // tensor-core form of conv1: rows = output channels, columns = taps (25 of 32 used)
+      // tensor-core form of conv1: rows = output channels, columns = K slots (25 of 32 used)
       std::vector<__half> whi(2 * 32 * 32, __float2half_rn(0.f)), wlo(2 * 32 * 32, __float2half_rn(0.f));
       for (int s = 0; s < 2; ++s) {
         float maxabs = 0.f;
@@ -371,12 +373,15 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
         }
         const float scale = ldexpf(1.0f, kexp);
         h->c1_inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
+        // K slot 6 * kh + kw (kw < 5); slots 5, 11, 17, 23, 29, 30, 31 stay zero (tc_conv1.cu: a kernel row = six consecutive
+        // input pixels, five taps and one zero-weight slot)
         for (int t = 0; t < 25; ++t)
           for (int c = 0; c < 32; ++c) {
             const float v = w[s * per + t * 32 + c] * scale;
             const __half hi = __float2half_rn(v);
-            whi[(s * 32 + c) * 32 + t] = hi;
-            wlo[(s * 32 + c) * 32 + t] = __float2half_rn(v - __half2float(hi));
+            const int kslot = 6 * (t / 5) + t % 5;
+            whi[(s * 32 + c) * 32 + kslot] = hi;
+            wlo[(s * 32 + c) * 32 + kslot] = __float2half_rn(v - __half2float(hi));
           }
       }
       if (int rc = upload(h, (void**)&h->c1_w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
@@ -608,6 +613,12 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     if (res && (res->Hs != out.Hs || res->Ws != out.Ws)) return fail(h, NNIC_ERR_CUDA, "internal: residual and output storage differ");
     pp.rows_per_set = L.rows_per_set;
     pp.inv_scale[0] = L.inv_scale[0]; pp.inv_scale[1] = L.inv_scale[1];
+    if (h->a_hi_only) {
+      // dconv1 on the integer symbols q: sum q*w is exact in the operands, and x = q/255 (decoder.py:40) enters as one factor of
+      // the epilogue scale, 2^-k / 255 rounded once -- a relative 2^-24, the size of the rounding of x itself
+      pp.a_hi_only = 1;
+      for (int s2 = 0; s2 < 2; ++s2) pp.inv_scale[s2] = (L.inv_scale[s2] * ACT_SCALE) / 255.0f;
+    }
     pp.bias = L.bias;
     pp.res_hi = res ? res->hi : nullptr; pp.res_lo = res ? res->lo : nullptr;
     pp.out_mode = out_mode;
@@ -747,14 +758,19 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   Act d2 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
   Act d3 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
   Act d4 = take_act(h, split, P, 4 * lh, 4 * lw, 64);
+  // u8 latent into the tensor-core decoder: the symbols go in as exact fp16 integers (one plane, one product less per MAC)
+  const bool int_latent = latent && split && !h->decode_fp16 && h->int_latent;
   if (latent) {
-    CKL(h, K_EXPAND, st, launch_latent_expand(latent, nb, lh, lw, d0.hi, d0.lo, d0.f32, st));
+    CKL(h, K_EXPAND, st, launch_latent_expand(latent, nb, lh, lw, d0.hi, d0.lo, d0.f32, int_latent, st));
   } else if (split) {
     CKL(h, K_F32_SPLIT, st, launch_f32_to_split(planes, (size_t)P * lh * lw * 32, d0.hi, d0.lo, st));
   } else {
     d0.f32 = const_cast<float*>(planes);
   }
-  if (int rc = run_gemm_layer(h, 1, 0, d0, d1, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
+  h->a_hi_only = int_latent;
+  const int rc_d1 = run_gemm_layer(h, 1, 0, d0, d1, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st);
+  h->a_hi_only = false;
+  if (rc_d1) return rc_d1;
   if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
@@ -849,6 +865,7 @@ int nnic_create(int device, nnic_t** out) {
   h->encode_tiled = (EncodeTiledFn)fn;
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_INT_LATENT")) h->int_latent = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env);
   if (const char* env = getenv("NNIC_TC_DBG")) h->tc_dbg = atoi(env);
   if (const char* env = getenv("NNIC_HIST_VARIANT")) h->hist_variant = atoi(env);

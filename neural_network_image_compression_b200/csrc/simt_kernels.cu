@@ -442,32 +442,44 @@ cudaError_t launch_dconv8(const __half* in_hi, const __half* in_lo, const float*
 // latent expand / split / quantise
 // =============================================================================================
 // Reference: Decoder.__call__ lines 40-41: x.astype(float32)/255 and tf.split into 3 x 32 channels.
-template <bool OUT_SPLIT>
+// OUT_KIND 0: f32 planes; 1: split fp16 planes of x/255; 2: one fp16 plane holding the integer symbols themselves (exact),
+// for the tensor-core dconv1, which folds the /255 into its epilogue scale (nnic_api.cu decode_batch).
+template <int OUT_KIND>
 __global__ void __launch_bounds__(256) k_latent_expand(const uint8_t* __restrict__ latent, int N, size_t pix,
                                                        __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                        float* __restrict__ out_f32) {
-  // one thread = 8 channels of one (pixel, plane); 12 threads per latent pixel
-  const size_t total = (size_t)N * pix * 12;
+  // one thread = 16 channels of one (pixel, plane): one 128-bit load; 6 threads per latent pixel
+  const size_t total = (size_t)N * pix * 6;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t gp = i / 12;              // n*pix + pixel
-    const int sub = (int)(i - gp * 12);    // 0..11 -> plane = sub/4, channel group = sub%4
-    const int plane = sub >> 2, cg = sub & 3;
+    const size_t gp = i / 6;               // n*pix + pixel
+    const int sub = (int)(i - gp * 6);     // 0..5 -> plane = sub/2, channel group = sub%2
+    const int plane = sub >> 1, cg = sub & 1;
     const size_t n = gp / pix, q = gp - n * pix;
-    const uint2 raw = *reinterpret_cast<const uint2*>(latent + gp * 96 + plane * 32 + cg * 8);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(latent + gp * 96 + plane * 32 + cg * 16));
     const uint8_t* s = reinterpret_cast<const uint8_t*>(&raw);
-    const size_t o = (((size_t)plane * N + n) * pix + q) * 32 + cg * 8;
-    float v[8];
+    const size_t o = (((size_t)plane * N + n) * pix + q) * 32 + cg * 16;
+    if (OUT_KIND == 2) {
+      __align__(16) __half h[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __fdiv_rn((float)s[e], 255.0f);
-    if (OUT_SPLIT) {
-      __align__(16) __half h[8], l[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_f32(v[e], h[e], l[e]);
+      for (int e = 0; e < 16; ++e) h[e] = __ushort2half_rn((unsigned short)s[e]);
       *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 8);
+      continue;
+    }
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __fdiv_rn((float)s[e], 255.0f);
+    if (OUT_KIND == 1) {
+      __align__(16) __half h[16], l[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) split_f32(v[e], h[e], l[e]);
+      *reinterpret_cast<uint4*>(out_hi + o) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(out_hi + o + 8) = *reinterpret_cast<uint4*>(h + 8);
       *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<uint4*>(l);
+      *reinterpret_cast<uint4*>(out_lo + o + 8) = *reinterpret_cast<uint4*>(l + 8);
     } else {
-      *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(out_f32 + o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
     }
   }
 }
@@ -479,11 +491,12 @@ static int grid_for(size_t work_items, int block) {
 }
 
 cudaError_t launch_latent_expand(const uint8_t* latent, int N, int lh, int lw, __half* out_hi, __half* out_lo,
-                                 float* out_f32, cudaStream_t stream) {
+                                 float* out_f32, bool integer_symbols, cudaStream_t stream) {
   const size_t pix = (size_t)lh * lw;
-  const int grid = grid_for((size_t)N * pix * 12, 256);
-  if (out_hi) k_latent_expand<true><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, out_lo, nullptr);
-  else k_latent_expand<false><<<grid, 256, 0, stream>>>(latent, N, pix, nullptr, nullptr, out_f32);
+  const int grid = grid_for((size_t)N * pix * 6, 256);
+  if (out_hi && integer_symbols) k_latent_expand<2><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, nullptr, nullptr);
+  else if (out_hi) k_latent_expand<1><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, out_lo, nullptr);
+  else k_latent_expand<0><<<grid, 256, 0, stream>>>(latent, N, pix, nullptr, nullptr, out_f32);
   return cudaGetLastError();
 }
 
@@ -541,9 +554,9 @@ cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t*
 // l % NC.  Shared-memory atomics serialise lanes of one instruction that hit the same ADDRESS or the same BANK; with the
 // copies interleaved, lanes that count the same symbol (a typical latent has ~50 distinct symbols, so many lanes do) land in
 // different banks, and two lanes collide only when they share a copy (32/NC lanes) and their bins differ by a multiple of
-// 32/NC.  Symbols 0 (about half of a typical latent) never touch the atomics: they are counted by subtraction.  Round 1's
-// per-warp tables (all 32 lanes in one copy) ran at 1.65 TB/s on the 805 MB latent of config 5; see DESIGN.md section 5
-// and profiles/r2_hist_variants.log for the copies / occupancy sweep.
+// 32/NC.  Symbols 0 (about half of a typical latent) never touch the atomics: they are counted by subtraction.  The sweep
+// over NC (profiles/r2_hist_variants.log) showed that collisions are NOT what bounds this pass -- see launch_hist -- so the
+// product runs NC = 1; the template stays for the measurement.
 constexpr int HIST_THREADS = 256;
 constexpr int HIST_CHUNK = 96 * 256;          // bytes per block-iteration: a multiple of 96 and of 16*256
 
@@ -632,14 +645,18 @@ static cudaError_t launch_hist_nc(const uint8_t* latent, int N, size_t bytes, in
 cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, int num_sms, int variant,
                         cudaStream_t stream) {
   const size_t bytes = pixels_per_image * 96;
-  // variant (development, NNIC_HIST_VARIANT): copies * 100 + resident blocks per SM; default 16 copies (48 KB), 4 blocks
-  const int nc = variant > 0 ? variant / 100 : 16, bps = variant > 0 ? variant % 100 : 4;
+  // variant (development, NNIC_HIST_VARIANT): copies * 100 + resident blocks per SM.  Default: one copy, 8 blocks per SM --
+  // measured on the 805 MB latent of config 5 (profiles/r2_hist_variants.log): 1 / 4 / 8 / 16 / 32 copies run at 2.0 / 1.97 /
+  // 1.93 / 1.77 / 1.13 TB/s, for a uniform, a geometric and a half-zero symbol distribution alike: the pass is bound by the
+  // issue rate of shared-memory atomic instructions (about one warp-wide ATOMS per 4.5 cycles per SM, whatever its lanes
+  // hit), not by address or bank collisions, so extra copies only cost occupancy and flush work.
+  const int nc = variant > 0 ? variant / 100 : 1, bps = variant > 0 ? variant % 100 : 8;
   switch (nc) {
-    case 1: return launch_hist_nc<1>(latent, N, bytes, num_sms, bps, hist, stream);
     case 4: return launch_hist_nc<4>(latent, N, bytes, num_sms, bps, hist, stream);
     case 8: return launch_hist_nc<8>(latent, N, bytes, num_sms, bps, hist, stream);
     case 32: return launch_hist_nc<32>(latent, N, bytes, num_sms, bps, hist, stream);
-    default: return launch_hist_nc<16>(latent, N, bytes, num_sms, bps, hist, stream);
+    case 16: return launch_hist_nc<16>(latent, N, bytes, num_sms, bps, hist, stream);
+    default: return launch_hist_nc<1>(latent, N, bytes, num_sms, bps, hist, stream);
   }
 }
 

@@ -78,7 +78,10 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
 // CL = thread-block cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring items in lockstep
 // and every weight tile is fetched from L2 once and MULTICAST into both shared memories (the CTAs alternate as the
 // issuer); a ring slot is refilled when the MMAs of both CTAs have released it.
-template <int RB, int NSPLIT, int COUT, bool FAST, int CL>
+// AHI: the input activations are EXACT in one fp16 plane (dconv1 fed with the integer latent symbols 0..255, see
+// nnic_api.cu decode_batch): no lo patch is loaded and the A_lo x W_hi product is not issued; everything else as in the
+// split arithmetic (A_hi x [W_hi | W_lo], main + correction halves, split output).
+template <int RB, int NSPLIT, int COUT, bool FAST, int CL, bool AHI>
 __global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -147,9 +150,9 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if ((prm.dbg & 16) || ((prm.dbg & 64) && it >= (int)blockIdx.x + NSETS * (int)gridDim.x)) {   // 64: only the first NSETS items load
             mbar_arrive(&patch_full[pb]);
           } else {
-            mbar_expect_tx(&patch_full[pb], FAST ? PATCH_TX : 2 * PATCH_TX);
+            mbar_expect_tx(&patch_full[pb], (FAST || AHI) ? PATCH_TX : 2 * PATCH_TX);
             tma_load_5d(&map_a_hi, pbuf, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
-            if (!FAST) tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
+            if (!FAST && !AHI) tma_load_5d(&map_a_lo, pbuf + PATCH_SLOT, &patch_full[pb], prm.patch_c0[q], X0 - 1, prm.patch_py[q], Y0 - 1, p);
           }
         }
         __syncwarp();
@@ -259,7 +262,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_narrow, accumulate);
                       } else {
                         umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, accumulate);
-                        umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+                        if (!AHI) umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
                       }
                       accumulate = 1u;
                     }
@@ -309,7 +312,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // accesses (one full 32-byte sector per thread and instruction)
         const int oY = tY0 + lg * 4 + (lane >> 3), oX = tX0 + (lane & 7);
         const int ooy = oY * prm.out_stride + prm.jobs[j].out_oy, oox = oX * prm.out_stride + prm.jobs[j].out_ox;
-        const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo;
+        const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo && !(prm.dbg & 2);
         const size_t ooff = (((size_t)p * prm.Hs + ooy) * prm.Ws + oox) * COUT + ch0;
         // residual: loaded now so that its latency hides behind the MMAs
         uint32_t res_h[HALF / 2], res_l[HALF / 2];
@@ -333,7 +336,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
           uint32_t vm[HALF], vc[HALF];
-          if (HALF == 32) { tmem_ld32_nowait(taddr, vm); if (!FAST) tmem_ld32_nowait(taddr + COUT, vc); }
+          if (prm.dbg & 8) {
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) { vm[i] = 0; vc[i] = 0; }
+          } else if (HALF == 32) { tmem_ld32_nowait(taddr, vm); if (!FAST) tmem_ld32_nowait(taddr + COUT, vc); }
           else { tmem_ld16_nowait(taddr, vm); if (!FAST) tmem_ld16_nowait(taddr + COUT, vc); }
           tmem_ld_wait();
           tc_fence_before();
@@ -448,12 +454,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1>
+template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1, bool AHI = false>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
   using Cfg = PCfg<RB, NSPLIT, COUT>;
-  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL>;
+  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL, AHI>;
   static unsigned long long attr_devices = 0;
   static int max_grid_of[64];                  // per device: CTAs that can be co-resident (persistent kernel: one wave)
   int dev = 0;
@@ -503,6 +509,10 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
     if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 128) return launch_patch_impl<128, 2, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 64) return launch_patch_impl<64, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (prm.a_hi_only) {                         // dconv1 on the integer latent symbols
+    if (row_bytes == 64 && prm.cout == 64 && prm.out_mode == TC_OUT_SPLIT) return launch_patch_impl<64, 4, 64, false, 1, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     return cudaErrorInvalidValue;
   }
   if (prm.cluster == 2) {                      // weight tiles multicast to CTA pairs

@@ -190,7 +190,8 @@ def compare(got: np.ndarray, rec: dict, prefix: str, first_image: int = 0) -> di
              "mismatch_vs_f64": int((at != s64).sum()), "mismatch_vs_f32": int((at != s32).sum()),
              "mismatch_outside_tie_band": 0 if not bad_images else None,
              "f32_oracle_vs_f64_oracle": mism32 if n == n_total else None,
-             "mismatch_fraction_vs_f64": float((at != s64).sum()) / flat.size}
+             "mismatch_fraction_vs_f64": float((at != s64).sum()) / flat.size,
+             "_flips_per_image": np.bincount(pos[at != s64] // per, minlength=n)}
     assert not bad_images, f"{prefix}: bytes outside the rounding-tie band differ from the fp64 oracle in images {bad_images[:8]}"
     assert bool(legal.all()), f"{prefix}: {int((~legal).sum())} tie bytes are neither floor nor floor+1"
     assert stats["mismatch_fraction_vs_f64"] <= MISMATCH_LIMIT, f"{prefix}: mismatch fraction {stats['mismatch_fraction_vs_f64']:.2e}"
