@@ -377,8 +377,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (valid) {
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {
+                if (prm.dbg & 128) { st_global_2xv4(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_2xv4(prm.out_lo + ooff + 16 * q, l + 8 * q); }
+                else if (prm.dbg & 256) { st_global_v8_cs(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_v8_cs(prm.out_lo + ooff + 16 * q, l + 8 * q); }
+                else {
                 st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
                 if (!FAST) st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
+                }
               }
             }
           } else if (prm.out_mode == TC_OUT_F32) {
