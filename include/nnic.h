@@ -166,6 +166,27 @@ int nnic_hist_allreduce(nnic_t* h, void* nccl_comm, uint64_t* hist_global, void*
 int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float* entropy_bits,
                              int mem_kind, void* stream);
 
+/* ---- forward extras of the training step ----------------------------------------------------
+ * The reference's training loop runs, beside encoder and decoder, three forward computations (tf2_0/src/training.py):
+ *
+ * nnic_entropynet_*: Entropynet (training.py:25-42), the CNN regressor of the PNG rate: Conv2D(64,5,2,SAME,leaky),
+ *   2 x Conv2D(64,3,1,SAME,leaky), Flatten, Dense(512), Dense(1), clip(0, 8), applied to the encoder's float output
+ *   `batch_encoded` [P,h,w,32] (P = 3N planes; ONE network for all planes).  Layers 0..4 = conv1, conv2, conv3 (Keras Conv2D
+ *   kernels [kh,kw,Cin,Cout]), dense1 (Keras Dense kernel [features,512], features = 64*ceil(h/2)*ceil(w/2), NHWC flatten order),
+ *   dense2 ([512,1]); `features` is only read for layer 3.  The convolutions run on the tensor-core convolution kernel
+ *   (FFMA kernels for odd h or w), the dense layers in fp32.  approx_entropy: float [P].
+ * nnic_noise_quantise: the quantisation proxy (training.py:87-88) out = clip(encoded + u/255, 0, 1), u ~ U(-0.5, 0.5).
+ *   `noise` (optional, `count` floats) supplies u; otherwise u is drawn from Philox4x32-10 keyed by `seed` and the element
+ *   index, so the result does not depend on the launch geometry or on the rank count.
+ * nnic_ssim: tf.image.ssim(a, b, max_val=1.0) (training.py:108,113) of single-channel float images [P,H,W] (H, W >= 11):
+ *   11x11 Gaussian window (sigma 1.5), k1 = 0.01, k2 = 0.03, mean over the (H-10) x (W-10) map.  ssim: float [P]. */
+int nnic_entropynet_set_weights(nnic_t* h, int layer, const float* kernel, const float* bias, int features);
+int nnic_entropynet_forward(nnic_t* h, const float* encoded, int P, int lh, int lw, float* approx_entropy, int mem_kind,
+                            void* stream);
+int nnic_noise_quantise(nnic_t* h, const float* encoded, size_t count, uint64_t seed, const float* noise, float* out,
+                        int mem_kind, void* stream);
+int nnic_ssim(nnic_t* h, const float* a, const float* b, int P, int H, int W, float* ssim, int mem_kind, void* stream);
+
 /* ---- scratch management ---------------------------------------------------------------------
  * Activation scratch is grown lazily and reused.  Images beyond `max_planes_in_flight` colour
  * planes are processed in micro-batches inside one call.  0 = library default. */
@@ -184,7 +205,7 @@ enum nnic_kernel_id {
   NNIC_KERNEL_CONV1 = 0, NNIC_KERNEL_CONV2, NNIC_KERNEL_CONV3, NNIC_KERNEL_CONV4, NNIC_KERNEL_CONV8,
   NNIC_KERNEL_QUANTISE, NNIC_KERNEL_EXPAND, NNIC_KERNEL_DCONV1, NNIC_KERNEL_DCONV5, NNIC_KERNEL_DCONV6,
   NNIC_KERNEL_DCONV7, NNIC_KERNEL_DCONV8, NNIC_KERNEL_HIST, NNIC_KERNEL_ENTROPY, NNIC_KERNEL_HIST_REDUCE,
-  NNIC_KERNEL_F32_SPLIT, NNIC_KERNEL_COUNT
+  NNIC_KERNEL_F32_SPLIT, NNIC_KERNEL_ENTROPYNET_CONV, NNIC_KERNEL_DENSE, NNIC_KERNEL_SSIM, NNIC_KERNEL_NOISE, NNIC_KERNEL_COUNT
 };
 int nnic_set_profiling(nnic_t* h, int on);
 int nnic_profile_collect(nnic_t* h, float* ms_per_kernel, int* launches_per_kernel, int capacity);

@@ -10,8 +10,9 @@ from .encoder import Encoder
 from .container import get_bpp, pack_latent, read_dataset, save_img, unpack_latent
 from .graph import GraphCodec
 from .rate import Rate, entropy_from_counts, rate, rate_channels
+from .training import Entropynet, entropynet_glorot, noisy_quantise, ssim
 from .utils import ProClass
 
-__all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "rate", "rate_channels", "Rate", "entropy_from_counts", "GraphCodec",
+__all__ = ["Encoder", "Decoder", "ProClass", "Handle", "NnicError", "Entropynet", "entropynet_glorot", "noisy_quantise", "ssim", "rate", "rate_channels", "Rate", "entropy_from_counts", "GraphCodec",
            "weights", "dist", "container", "colour_constants", "load_library", "pack_latent", "unpack_latent", "read_dataset",
            "save_img", "get_bpp"]

@@ -43,6 +43,10 @@ SYMBOLS = (
     ("nnic_set_decode_precision", C.c_int, (_vp, C.c_int)),
     ("nnic_get_decode_precision", C.c_int, (_vp,)),
     ("nnic_entropy_from_counts", C.c_int, (_vp, _vp, C.c_int, _vp, C.c_int, _vp)),
+    ("nnic_entropynet_set_weights", C.c_int, (_vp, C.c_int, _vp, _vp, C.c_int)),
+    ("nnic_entropynet_forward", C.c_int, (_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
+    ("nnic_noise_quantise", C.c_int, (_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, C.c_int, _vp)),
+    ("nnic_ssim", C.c_int, (_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp)),
     ("nnic_set_micro_batch", C.c_int, (_vp, C.c_int)),
     ("nnic_scratch_bytes", C.c_size_t, (_vp,)),
     ("nnic_set_profiling", C.c_int, (_vp, C.c_int)),
@@ -53,7 +57,7 @@ SYMBOLS = (
 
 # include/nnic.h enum nnic_kernel_id
 KERNEL_NAMES = ("conv1", "conv2", "conv3", "conv4", "conv8", "quantise", "latent_expand", "dconv1", "dconv5",
-                "dconv6", "dconv7", "dconv8", "hist", "entropy", "hist_reduce", "f32_split")
+                "dconv6", "dconv7", "dconv8", "hist", "entropy", "hist_reduce", "f32_split", "entropynet_conv", "dense", "ssim", "noise")
 
 _lib = None
 

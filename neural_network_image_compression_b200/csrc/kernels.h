@@ -80,6 +80,19 @@ cudaError_t launch_entropy_u32(const uint32_t* hist, int N, float symbols_per_pl
 cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float* entropy,
                                cudaStream_t stream);
 
+// ---- forward-only extras of the reference's training step (train_extras.cu; tf2_0/src/training.py:25-42, 87-88, 108-119) ----
+// Dense(512) on [P][F] inputs given as split fp16 planes (x_hi / x_lo) or fp32 (x_f32); Wt is the Keras kernel [F][512]
+cudaError_t launch_dense512(const __half* x_hi, const __half* x_lo, const float* x_f32, int P, int F, const float* Wt,
+                            const float* bias, float* out, cudaStream_t stream);
+// Dense(1) + clip(0, 8): hid [P][512] -> out [P]
+cudaError_t launch_dense1_clip(const float* hid, int P, const float* w, float b, float* out, cudaStream_t stream);
+// out = clip(x + u/255, 0, 1); u from `noise` (optional) or Philox4x32-10(seed, element index)
+cudaError_t launch_noise_quantise(const float* x, size_t count, unsigned long long seed, const float* noise, float* out,
+                                  int num_sms, cudaStream_t stream);
+// tf.image.ssim(a, b, max_val=1) of fp32 [P][H][W] images; partial: scratch of ssim_partial_count floats
+cudaError_t launch_ssim(const float* a, const float* b, int P, int H, int W, float* partial, float* out, cudaStream_t stream);
+size_t ssim_partial_count(int P, int H, int W);
+
 // ---- tensor-core convolutions ------------------------------------------------------------------------
 enum TcOutMode { TC_OUT_SPLIT = 0, TC_OUT_F32 = 1, TC_OUT_QUANT = 2 };
 

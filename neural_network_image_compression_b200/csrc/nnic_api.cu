@@ -28,13 +28,19 @@ const LayerSpec kEnc[5] = {{"conv1", 5, 2, 1, 32, false}, {"conv2", 5, 2, 32, 64
                            {"conv4", 3, 1, 64, 64, false}, {"conv8", 5, 2, 64, 32, false}};
 const LayerSpec kDec[5] = {{"dconv1", 5, 2, 32, 64, true}, {"dconv5", 3, 1, 64, 64, true}, {"dconv6", 3, 1, 64, 64, true},
                            {"dconv7", 5, 2, 64, 64, true}, {"dconv8", 5, 2, 64, 1, true}};
+// Entropynet (tf2_0/src/training.py:25-33): the three convolutions of the rate regressor; same layer types as conv2 / conv3
+const LayerSpec kEnt[3] = {{"entropynet.conv1", 5, 2, 32, 64, false}, {"entropynet.conv2", 3, 1, 64, 64, false},
+                           {"entropynet.conv3", 3, 1, 64, 64, false}};
 inline const LayerSpec& spec_of(int set, int layer) { return set < 2 ? kEnc[layer] : kDec[layer]; }
+// GEMM-shaped layer `gi` of network `net` (0 encoder: conv2, conv3, conv4, conv8; 1 decoder: dconv1, dconv5, dconv6, dconv7;
+// 2 Entropynet: conv1, conv2, conv3)
+inline const LayerSpec& gemm_spec(int net, int gi) { return net == 0 ? kEnc[gi + 1] : (net == 1 ? kDec[gi] : kEnt[gi]); }
 
 thread_local std::string g_global_error = "";
 
 // kernel ids reported by nnic_profile_collect (keep in sync with include/nnic.h NNIC_KERNEL_*)
 enum { K_CONV1 = 0, K_CONV2, K_CONV3, K_CONV4, K_CONV8, K_QUANTISE, K_EXPAND, K_DCONV1, K_DCONV5, K_DCONV6, K_DCONV7,
-       K_DCONV8, K_HIST, K_ENTROPY, K_HIST_REDUCE, K_F32_SPLIT, K_COUNT };
+       K_DCONV8, K_HIST, K_ENTROPY, K_HIST_REDUCE, K_F32_SPLIT, K_ENT_CONV, K_DENSE, K_SSIM, K_NOISE, K_COUNT };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -104,7 +110,7 @@ struct nnic_handle {
   // device weights: index 0 = encoder, 1 = decoder
   std::vector<float> w_edge[2];            // host: conv1 [2][25][32] / dconv8 [2][25][64] (passed as kernel parameters)
   std::vector<float> b_edge[2];            // host: [2][32] / [2][1]
-  TcLayer tc[2][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7
+  TcLayer tc[3][4];                        // encoder conv2,3,4,8 ; decoder dconv1,5,6,7 ; Entropynet conv1,2,3
   // conv1 on the tensor cores: [2 sets][32 channels][32 taps] fp16 hi/lo, bias [2][32]
   __half* c1_w_hi = nullptr; __half* c1_w_lo = nullptr; float* c1_bias = nullptr;
   float c1_inv_scale[2] = {1.f, 1.f};
@@ -113,7 +119,13 @@ struct nnic_handle {
   __half* d8_w_hi = nullptr; __half* d8_w_lo = nullptr;
   CUtensorMap d8_map_w_hi, d8_map_w_lo;
   float d8_inv_scale[2] = {1.f, 1.f};
-  SimtLayer simt[2][4];
+  SimtLayer simt[3][4];
+  // Entropynet (training.py:25-42): host copies of conv1..3 (Keras HWIO), dense1 [F,512], dense2 [512,1]; device dense weights
+  std::vector<float> ent_kernel[5], ent_bias[5];
+  bool ent_have[5] = {};
+  bool ent_dirty = true;
+  int ent_features = 0;                    // F = rows of dense1's kernel
+  float* ent_d1_w = nullptr; float* ent_d1_b = nullptr; float* ent_d2_w = nullptr; float ent_d2_b = 0.f;
 
   // host-buffer calls: copies run on two internal streams and overlap the kernels of neighbouring micro-batches
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -337,6 +349,62 @@ int upload(nnic_t* h, void** dst, const void* src, size_t bytes) {
   return 0;
 }
 
+// Device forms of one GEMM-shaped layer for both weight sets: fp32 tap-major copies for the FFMA path and the fp16 hi/lo
+// matrices + tensor maps of the tensor-core path.
+int build_gemm_layer(nnic_t* h, const LayerSpec& sp, const std::vector<float>* const kerns[2], const std::vector<float>* const biases[2],
+                     TcLayer& L, SimtLayer& S) {
+    // --- fp32 tap-major copies for the FFMA path: [set][tap][ci][co]
+    {
+      const size_t per = (size_t)sp.k * sp.k * sp.cin * sp.cout;
+      std::vector<float> w(2 * per), b(2 * sp.cout);
+      for (int s = 0; s < 2; ++s) {
+        const std::vector<float>& kern = *kerns[s];
+        for (int a = 0; a < sp.k; ++a) for (int bb = 0; bb < sp.k; ++bb)
+          for (int ci = 0; ci < sp.cin; ++ci) for (int co = 0; co < sp.cout; ++co)
+            w[s * per + (((size_t)a * sp.k + bb) * sp.cin + ci) * sp.cout + co] = kval(sp, kern, a, bb, ci, co);
+        memcpy(&b[s * sp.cout], biases[s]->data(), sp.cout * sizeof(float));
+      }
+      if (int rc = upload(h, (void**)&S.w, w.data(), w.size() * 4)) return rc;
+      if (int rc = upload(h, (void**)&S.bias, b.data(), b.size() * 4)) return rc;
+    }
+    // --- tensor-core matrices: fp16 hi/lo of w * 2^kexp, [set][rows][kslab]
+    build_tc_program(sp, L);
+    const size_t per = (size_t)L.rows_per_set * L.kslab;
+    std::vector<__half> whi(2 * per), wlo(2 * per);
+    std::vector<float> b(2 * sp.cout);
+    for (int s = 0; s < 2; ++s) {
+      const std::vector<float>& kern = *kerns[s];
+      float maxabs = 0.f;
+      for (float v : kern) maxabs = fmaxf(maxabs, fabsf(v));
+      int kexp = 0;
+      if (maxabs > 0.f && std::isfinite(maxabs)) {
+        kexp = (int)floorf(log2f(32768.0f / maxabs));
+        if (kexp < -14) kexp = -14;
+        if (kexp > 24) kexp = 24;
+      }
+      const float scale = ldexpf(1.0f, kexp);
+      L.inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
+      for (int r = 0; r < L.rows_per_set; ++r)
+        for (int c = 0; c < L.kslab; ++c) {
+          const float v = tc_weight_at(sp, kern, r, c) * scale;
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          whi[s * per + (size_t)r * L.kslab + c] = hi;
+          wlo[s * per + (size_t)r * L.kslab + c] = lo;
+        }
+      memcpy(&b[s * sp.cout], biases[s]->data(), sp.cout * sizeof(float));
+    }
+    if (int rc = upload(h, (void**)&L.w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
+    if (int rc = upload(h, (void**)&L.w_lo, wlo.data(), wlo.size() * sizeof(__half))) return rc;
+    if (int rc = upload(h, (void**)&L.bias, b.data(), b.size() * 4)) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)L.kslab, (cuuint64_t)2 * L.rows_per_set};
+    cuuint64_t strides[1] = {(cuuint64_t)L.kslab * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kslab, (cuuint32_t)L.cout};
+    if (int rc = make_map(h, &L.map_w_hi, L.w_hi, 2, dims, strides, box, L.row_bytes)) return rc;
+    if (int rc = make_map(h, &L.map_w_lo, L.w_lo, 2, dims, strides, box, L.row_bytes)) return rc;
+  return 0;
+}
+
 int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
   bool& dirty = net == 0 ? h->dirty_enc : h->dirty_dec;
   if (!dirty) return 0;
@@ -421,57 +489,9 @@ int finalize_weights(nnic_t* h, int net /*0 enc, 1 dec*/) {
   }
   for (int gi = 0; gi < 4; ++gi) {
     const int l = net == 0 ? gi + 1 : gi;
-    const LayerSpec& sp = spec_of(set0, l);
-    // --- fp32 tap-major copies for the FFMA path: [set][tap][ci][co]
-    {
-      const size_t per = (size_t)sp.k * sp.k * sp.cin * sp.cout;
-      std::vector<float> w(2 * per), b(2 * sp.cout);
-      for (int s = 0; s < 2; ++s) {
-        const std::vector<float>& kern = h->kernel[set0 + s][l];
-        for (int a = 0; a < sp.k; ++a) for (int bb = 0; bb < sp.k; ++bb)
-          for (int ci = 0; ci < sp.cin; ++ci) for (int co = 0; co < sp.cout; ++co)
-            w[s * per + (((size_t)a * sp.k + bb) * sp.cin + ci) * sp.cout + co] = kval(sp, kern, a, bb, ci, co);
-        memcpy(&b[s * sp.cout], h->bias[set0 + s][l].data(), sp.cout * sizeof(float));
-      }
-      if (int rc = upload(h, (void**)&h->simt[net][gi].w, w.data(), w.size() * 4)) return rc;
-      if (int rc = upload(h, (void**)&h->simt[net][gi].bias, b.data(), b.size() * 4)) return rc;
-    }
-    // --- tensor-core matrices: fp16 hi/lo of w * 2^kexp, [set][rows][kslab]
-    TcLayer& L = h->tc[net][gi];
-    build_tc_program(sp, L);
-    const size_t per = (size_t)L.rows_per_set * L.kslab;
-    std::vector<__half> whi(2 * per), wlo(2 * per);
-    std::vector<float> b(2 * sp.cout);
-    for (int s = 0; s < 2; ++s) {
-      const std::vector<float>& kern = h->kernel[set0 + s][l];
-      float maxabs = 0.f;
-      for (float v : kern) maxabs = fmaxf(maxabs, fabsf(v));
-      int kexp = 0;
-      if (maxabs > 0.f && std::isfinite(maxabs)) {
-        kexp = (int)floorf(log2f(32768.0f / maxabs));
-        if (kexp < -14) kexp = -14;
-        if (kexp > 24) kexp = 24;
-      }
-      const float scale = ldexpf(1.0f, kexp);
-      L.inv_scale[s] = ldexpf(1.0f, -kexp) * ACT_INV_SCALE;
-      for (int r = 0; r < L.rows_per_set; ++r)
-        for (int c = 0; c < L.kslab; ++c) {
-          const float v = tc_weight_at(sp, kern, r, c) * scale;
-          const __half hi = __float2half_rn(v);
-          const __half lo = __float2half_rn(v - __half2float(hi));
-          whi[s * per + (size_t)r * L.kslab + c] = hi;
-          wlo[s * per + (size_t)r * L.kslab + c] = lo;
-        }
-      memcpy(&b[s * sp.cout], h->bias[set0 + s][l].data(), sp.cout * sizeof(float));
-    }
-    if (int rc = upload(h, (void**)&L.w_hi, whi.data(), whi.size() * sizeof(__half))) return rc;
-    if (int rc = upload(h, (void**)&L.w_lo, wlo.data(), wlo.size() * sizeof(__half))) return rc;
-    if (int rc = upload(h, (void**)&L.bias, b.data(), b.size() * 4)) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)L.kslab, (cuuint64_t)2 * L.rows_per_set};
-    cuuint64_t strides[1] = {(cuuint64_t)L.kslab * 2};
-    cuuint32_t box[2] = {(cuuint32_t)L.kslab, (cuuint32_t)L.cout};
-    if (int rc = make_map(h, &L.map_w_hi, L.w_hi, 2, dims, strides, box, L.row_bytes)) return rc;
-    if (int rc = make_map(h, &L.map_w_lo, L.w_lo, 2, dims, strides, box, L.row_bytes)) return rc;
+    const std::vector<float>* kern[2] = {&h->kernel[set0][l], &h->kernel[set0 + 1][l]};
+    const std::vector<float>* bias[2] = {&h->bias[set0][l], &h->bias[set0 + 1][l]};
+    if (int rc = build_gemm_layer(h, spec_of(set0, l), kern, bias, h->tc[net][gi], h->simt[net][gi])) return rc;
   }
   dirty = false;
   return 0;
@@ -549,8 +569,8 @@ int check_device_error(nnic_t* h) {
 // one GEMM-shaped layer in either arithmetic
 int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, const Act* res, int P, int n_split,
                    int out_mode, uint8_t* out_u8, float* out_prequant, float* out_f32_planes, cudaStream_t st) {
-  const int l = net == 0 ? gi + 1 : gi;
-  const LayerSpec& sp = spec_of(net * 2, l);
+  const LayerSpec& sp = gemm_spec(net, gi);
+  const int kid = net == 0 ? K_CONV2 + gi : (net == 1 ? K_DCONV1 + gi : K_ENT_CONV);
   int Ho, Wo, Hp, Wp;
   if (!sp.transposed) { int pt; same_pad(in.H, sp.k, sp.s, Ho, pt); same_pad(in.W, sp.k, sp.s, Wo, pt); Hp = Ho; Wp = Wo; }
   else { Ho = in.H * sp.s; Wo = in.W * sp.s; Hp = in.H; Wp = in.W; }
@@ -559,7 +579,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     build_simt_jobs(sp, in.H, in.W, J);
     float* dst = out_mode == TC_OUT_F32 && out_f32_planes ? out_f32_planes : out.f32;
     const int clamp = (net == 0 && gi == 3) ? 1 : 0;
-    CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st, launch_simt_conv(sp.cin, sp.cout, in.f32, P, in.H, in.W, dst, Ho, Wo, Hp, Wp, h->simt[net][gi].w, sp.k * sp.k,
+    CKL(h, kid, st, launch_simt_conv(sp.cin, sp.cout, in.f32, P, in.H, in.W, dst, Ho, Wo, Hp, Wp, h->simt[net][gi].w, sp.k * sp.k,
                             h->simt[net][gi].bias, res ? res->f32 : nullptr, J, n_split, clamp, st));
     return 0;
   }
@@ -640,7 +660,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       CK(h, cudaMemsetAsync(h->tc_prof_buf, 0, prof_words * sizeof(long long), st));
       pp.dbg_buf = h->tc_prof_buf;
     }
-    CKL(h, (net == 0 ? K_CONV2 : K_DCONV1) + gi, st,
+    CKL(h, kid, st,
         launch_tc_conv_patch(L.row_bytes, *pa_hi, *pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
     if (prof) {
       std::vector<long long> hb(prof_words);
@@ -651,7 +671,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       for (int b = 0; b < nb_; ++b) for (int r = 0; r < 4; ++r) for (int k = 0; k < 8; ++k) a[r][k] += hb[((size_t)b * 4 + r) * 8 + k] / (double)nb_;
       fprintf(stderr, "[tcprof %s] producer: total %.0f wait_patch_empty %.0f wait_w_empty %.0f | mmaA: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | "
               "mmaB: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | epi: total %.0f wait_full %.0f tmem+add %.0f out %.0f\n",
-              spec_of(net * 2, l).name, a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[1][3], a[1][4], a[2][0], a[2][1], a[2][2], a[2][3], a[2][4],
+              sp.name, a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[1][3], a[1][4], a[2][0], a[2][1], a[2][2], a[2][3], a[2][4],
               a[3][0], a[3][1], a[3][2], a[3][3]);
     }
     return 0;
@@ -776,7 +796,7 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (split && h->tc_dconv8) {
     const CUtensorMap *ma_hi = nullptr, *ma_lo = nullptr;
-    if (int rc = cached_act_maps(h, 8, &ma_hi, &ma_lo, d4.hi, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
+    if (int rc = cached_act_maps(h, 15, &ma_hi, &ma_lo, d4.hi, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
     TcDconv8Params dp;
     memset(&dp, 0, sizeof dp);
     dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
@@ -814,6 +834,28 @@ size_t enc_act_need(bool split, size_t P, int H, int W) {
 size_t dec_act_need(bool split, size_t P, int lh, int lw) {
   return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
 }
+
+// ---- Entropynet (tf2_0/src/training.py:25-42) -------------------------------------------------------------------
+int finalize_entropynet(nnic_t* h) {
+  if (!h->ent_dirty) return 0;
+  static const char* names[5] = {"conv1", "conv2", "conv3", "dense1", "dense2"};
+  for (int l = 0; l < 5; ++l)
+    if (!h->ent_have[l]) return fail(h, NNIC_ERR_NO_WEIGHTS, "Entropynet weights of layer %s are not set", names[l]);
+  CK(h, cudaDeviceSynchronize());
+  for (int gi = 0; gi < 3; ++gi) {               // one network for every plane: both weight "sets" hold the same kernel
+    const std::vector<float>* kern[2] = {&h->ent_kernel[gi], &h->ent_kernel[gi]};
+    const std::vector<float>* bias[2] = {&h->ent_bias[gi], &h->ent_bias[gi]};
+    if (int rc = build_gemm_layer(h, kEnt[gi], kern, bias, h->tc[2][gi], h->simt[2][gi])) return rc;
+  }
+  if (h->ent_d1_w) { cudaFree(h->ent_d1_w); h->ent_d1_w = nullptr; }       // its size follows the feature count
+  if (int rc = upload(h, (void**)&h->ent_d1_w, h->ent_kernel[3].data(), h->ent_kernel[3].size() * 4)) return rc;
+  if (int rc = upload(h, (void**)&h->ent_d1_b, h->ent_bias[3].data(), 512 * 4)) return rc;
+  if (int rc = upload(h, (void**)&h->ent_d2_w, h->ent_kernel[4].data(), 512 * 4)) return rc;
+  h->ent_d2_b = h->ent_bias[4][0];
+  h->ent_dirty = false;
+  return 0;
+}
+
 
 // NNIC_MEM_DEVICE buffers must be device (or managed) memory of the handle's GPU: a host pointer or another GPU's memory
 // would fault inside a kernel, so it is rejected before anything is enqueued.  NULL (optional outputs) passes.
@@ -893,13 +935,14 @@ void nnic_destroy(nnic_t* h) {
   if (!h) return;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  for (int n = 0; n < 2; ++n) {
+  for (int n = 0; n < 3; ++n) {
     for (int i = 0; i < 4; ++i) {
       cudaFree(h->tc[n][i].w_hi); cudaFree(h->tc[n][i].w_lo); cudaFree(h->tc[n][i].bias);
       cudaFree(h->simt[n][i].w); cudaFree(h->simt[n][i].bias);
     }
   }
   cudaFree(h->d8_w_hi); cudaFree(h->d8_w_lo);
+  cudaFree(h->ent_d1_w); cudaFree(h->ent_d1_b); cudaFree(h->ent_d2_w);
   cudaFree(h->c1_w_hi); cudaFree(h->c1_w_lo); cudaFree(h->c1_bias);
   cudaFree(h->arena.ptr); cudaFree(h->rate_scratch.ptr); cudaFree(h->tc_prof_buf);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -1299,6 +1342,135 @@ int nnic_entropy_from_counts(nnic_t* h, const uint64_t* counts, int rows, float*
   CKL(h, K_ENTROPY, st, launch_entropy_u64(d_c, rows, d_e, st));
   CK(h, cudaMemcpyAsync(entropy_bits, d_e, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
   CK(h, cudaStreamSynchronize(st));
+  return NNIC_OK;
+}
+
+// ---- forward-only extras of the reference's training step -----------------------------------------
+
+int nnic_entropynet_set_weights(nnic_t* h, int layer, const float* kernel, const float* bias, int features) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (layer < 0 || layer > 4 || !kernel || !bias) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_entropynet_set_weights: bad layer %d or NULL buffer", layer);
+  size_t nk, nb;
+  if (layer < 3) { nk = (size_t)kEnt[layer].k * kEnt[layer].k * kEnt[layer].cin * kEnt[layer].cout; nb = kEnt[layer].cout; }
+  else if (layer == 3) {
+    if (features <= 0 || features % 64) return fail(h, NNIC_ERR_INVALID_ARG, "dense1 needs features = 64 * ceil(h/2) * ceil(w/2), got %d", features);
+    nk = (size_t)features * 512; nb = 512; h->ent_features = features;
+  } else { nk = 512; nb = 1; }
+  h->ent_kernel[layer].assign(kernel, kernel + nk);
+  h->ent_bias[layer].assign(bias, bias + nb);
+  h->ent_have[layer] = true;
+  h->ent_dirty = true;
+  return NNIC_OK;
+}
+
+int nnic_entropynet_forward(nnic_t* h, const float* encoded, int P, int lh, int lw, float* approx_entropy, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!encoded || !approx_entropy) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_entropynet_forward: NULL buffer");
+  if (P <= 0 || lh <= 0 || lw <= 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_entropynet_forward: non-positive shape");
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"encoded", encoded}, {"approx_entropy", approx_entropy}})) return rc;
+  if (int rc = check_device_error(h)) return rc;
+  if (int rc = finalize_entropynet(h)) return rc;
+  const int h2 = (lh + 1) / 2, w2 = (lw + 1) / 2;
+  const int F = h2 * w2 * 64;
+  if (F != h->ent_features)
+    return fail(h, NNIC_ERR_SHAPE, "Entropynet.dense1 was built for %d features; a %dx%d latent flattens to %d (training.py:30-31: Flatten -> Dense(512))", h->ent_features, lh, lw, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the stride-2 first layer reads its input through the parity view (even extents): odd latent sizes take the FFMA kernels
+  const int saved_arith = h->arith;
+  if ((lh | lw) & 1) h->arith = NNIC_ARITH_SIMT_F32;
+  const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  const size_t in_elems = (size_t)P * lh * lw * 32;
+  size_t need = act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, h2, w2, 64) + pad1k((size_t)P * 512 * 4) + pad1k((size_t)P * 4) + 16384;
+  if (host) need += pad1k(in_elems * 4);
+  int rc = ensure_buf(h, h->arena, need);
+  if (rc) { h->arith = saved_arith; return rc; }
+  h->arena_used = 0;
+  auto run = [&]() -> int {
+    const float* d_in = encoded;
+    if (host) {
+      float* t = (float*)arena_take(h, in_elems * 4);
+      CK(h, cudaMemcpyAsync(t, encoded, in_elems * 4, cudaMemcpyHostToDevice, st));
+      d_in = t;
+    }
+    Act a0 = take_act(h, split, P, lh, lw, 32);
+    Act a1 = take_act(h, split, P, h2, w2, 64), a2 = take_act(h, split, P, h2, w2, 64), a3 = take_act(h, split, P, h2, w2, 64);
+    float* hid = (float*)arena_take(h, (size_t)P * 512 * 4);
+    float* d_out = host ? (float*)arena_take(h, (size_t)P * 4) : approx_entropy;
+    if (split) CKL(h, K_F32_SPLIT, st, launch_f32_to_split(d_in, in_elems, a0.hi, a0.lo, st));
+    else a0.f32 = const_cast<float*>(d_in);
+    if (int r2 = run_gemm_layer(h, 2, 0, a0, a1, nullptr, P, P, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return r2;
+    if (int r2 = run_gemm_layer(h, 2, 1, a1, a2, nullptr, P, P, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return r2;
+    if (int r2 = run_gemm_layer(h, 2, 2, a2, a3, nullptr, P, P, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return r2;
+    CKL(h, K_DENSE, st, launch_dense512(a3.hi, a3.lo, a3.f32, P, F, h->ent_d1_w, h->ent_d1_b, hid, st));
+    CKL(h, K_DENSE, st, launch_dense1_clip(hid, P, h->ent_d2_w, h->ent_d2_b, d_out, st));
+    if (host) {
+      CK(h, cudaMemcpyAsync(approx_entropy, d_out, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+      CK(h, cudaStreamSynchronize(st));
+      if (int r2 = check_device_error(h)) return r2;
+    }
+    return 0;
+  };
+  rc = run();
+  h->arith = saved_arith;
+  if (rc && host) cudaStreamSynchronize(st);
+  return rc;
+}
+
+int nnic_noise_quantise(nnic_t* h, const float* encoded, size_t count, uint64_t seed, const float* noise, float* out, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!encoded || !out || count == 0) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_noise_quantise: NULL buffer or empty input");
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"encoded", encoded}, {"noise", noise}, {"out", out}})) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mem_kind == NNIC_MEM_DEVICE) {
+    CKL(h, K_NOISE, st, launch_noise_quantise(encoded, count, seed, noise, out, h->num_sms, st));
+    return NNIC_OK;
+  }
+  if (int rc = ensure_buf(h, h->arena, (noise ? 3 : 2) * pad1k(count * 4) + 8192)) return rc;
+  h->arena_used = 0;
+  float* d_x = (float*)arena_take(h, count * 4);
+  float* d_o = (float*)arena_take(h, count * 4);
+  float* d_n = noise ? (float*)arena_take(h, count * 4) : nullptr;
+  CK(h, cudaMemcpyAsync(d_x, encoded, count * 4, cudaMemcpyHostToDevice, st));
+  if (noise) CK(h, cudaMemcpyAsync(d_n, noise, count * 4, cudaMemcpyHostToDevice, st));
+  CKL(h, K_NOISE, st, launch_noise_quantise(d_x, count, seed, d_n, d_o, h->num_sms, st));
+  CK(h, cudaMemcpyAsync(out, d_o, count * 4, cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  return NNIC_OK;
+}
+
+int nnic_ssim(nnic_t* h, const float* a, const float* b, int P, int H, int W, float* ssim, int mem_kind, void* stream) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  if (!a || !b || !ssim) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_ssim: NULL buffer");
+  if (P <= 0 || H < 11 || W < 11) return fail(h, NNIC_ERR_INVALID_ARG, "nnic_ssim: images must be at least 11 x 11 (the window of tf.image.ssim), got %d x %d x %d", P, H, W);
+  if (mem_kind != NNIC_MEM_HOST && mem_kind != NNIC_MEM_DEVICE) return fail(h, NNIC_ERR_INVALID_ARG, "bad mem_kind %d", mem_kind);
+  DeviceGuard g(h->device);
+  if (int rc = check_device_ptrs(h, mem_kind, {{"a", a}, {"b", b}, {"ssim", ssim}})) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool host = mem_kind == NNIC_MEM_HOST;
+  const size_t elems = (size_t)P * H * W, npart = ssim_partial_count(P, H, W);
+  if (int rc = ensure_buf(h, h->rate_scratch, pad1k(npart * 4) + (host ? 2 * pad1k(elems * 4) + pad1k((size_t)P * 4) : 0) + 8192)) return rc;
+  uint8_t* base = (uint8_t*)h->rate_scratch.ptr;
+  float* d_part = (float*)base;
+  const float *d_a = a, *d_b = b;
+  float* d_out = ssim;
+  if (host) {
+    float* ta = (float*)(base + pad1k(npart * 4));
+    float* tb = (float*)(base + pad1k(npart * 4) + pad1k(elems * 4));
+    d_out = (float*)(base + pad1k(npart * 4) + 2 * pad1k(elems * 4));
+    CK(h, cudaMemcpyAsync(ta, a, elems * 4, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(tb, b, elems * 4, cudaMemcpyHostToDevice, st));
+    d_a = ta; d_b = tb;
+  }
+  CKL(h, K_SSIM, st, launch_ssim(d_a, d_b, P, H, W, d_part, d_out, st));
+  if (host) {
+    CK(h, cudaMemcpyAsync(ssim, d_out, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+  }
   return NNIC_OK;
 }
 

@@ -277,3 +277,49 @@ def unpack_latent(picture_u8: np.ndarray):
 def psnr(a_u8: np.ndarray, b_u8: np.ndarray):
     mse = np.mean((a_u8.astype(np.float64) - b_u8.astype(np.float64)) ** 2)
     return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+# ---- forward extras of the training step -----------------------------------------------------------
+def entropynet(x: np.ndarray, w: dict, mode: str = "f32"):
+    """tf2_0/src/training.py:25-42.  x [P,h,w,32] -> [P,1]: three SAME convolutions with leaky_relu, Flatten (NHWC order),
+    Dense(512), Dense(1) (both linear), clip(0, 8)."""
+    dt = _np_dtype(mode)
+    v = np.asarray(x, dt)
+    for name, s in (("conv1", 2), ("conv2", 1), ("conv3", 1)):
+        v = leaky_relu(conv2d_same(v, w[name + "/kernel"], w[name + "/bias"], s, mode))
+    v = v.reshape(v.shape[0], -1)
+    v = v @ np.asarray(w["dense1/kernel"], dt) + np.asarray(w["dense1/bias"], dt)
+    v = v @ np.asarray(w["dense2/kernel"], dt) + np.asarray(w["dense2/bias"], dt)
+    return np.clip(v, 0, 8)
+
+
+def noisy_quantise(encoded: np.ndarray, noise: np.ndarray, mode: str = "f32"):
+    """training.py:87-88 with the uniform draw passed in: clip(encoded + noise / 255, 0, 1), noise in [-0.5, 0.5)."""
+    dt = _np_dtype(mode)
+    return np.clip(np.asarray(encoded, dt) + np.asarray(noise, dt) / dt(255), 0, 1)
+
+
+def ssim(a: np.ndarray, b: np.ndarray, mode: str = "f32"):
+    """tf.image.ssim(a, b, max_val=1.0) for [P,H,W,1] images (training.py:108,113), following TensorFlow's published
+    definition (image_ops_impl._ssim_per_channel / _ssim_helper): an 11 x 11 Gaussian window (sigma 1.5, softmax-normalised),
+    VALID depthwise filtering of x, y, x*y and x*x + y*y, c1 = (0.01)^2, c2 = (0.03)^2,
+    luminance = (2 m0 m1 + c1) / (m0^2 + m1^2 + c1), cs = (2 E[xy] - 2 m0 m1 + c2) / (E[x^2 + y^2] - m0^2 - m1^2 + c2),
+    ssim = mean over the map of luminance * cs.  The 2-D window is applied as written (121 taps), not separably."""
+    dt = _t_dtype(mode)
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(dt).reshape(a.shape[0], 1, a.shape[1], a.shape[2])
+    y = torch.from_numpy(np.ascontiguousarray(b)).to(dt).reshape(b.shape[0], 1, b.shape[1], b.shape[2])
+    coords = torch.arange(11, dtype=dt) - 5.0
+    g = -0.5 * coords ** 2 / (1.5 ** 2)
+    k2d = torch.softmax((g.reshape(1, -1) + g.reshape(-1, 1)).reshape(-1), dim=0).reshape(1, 1, 11, 11)
+
+    def red(t):
+        return F.conv2d(t, k2d)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    m0, m1 = red(x), red(y)
+    num0 = m0 * m1 * 2.0
+    den0 = m0 * m0 + m1 * m1
+    lum = (num0 + c1) / (den0 + c1)
+    num1 = red(x * y) * 2.0
+    den1 = red(x * x + y * y)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (lum * cs).mean(dim=(1, 2, 3)).numpy()
