@@ -377,6 +377,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (valid) {
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {
+                if (prm.dbg & 512) {             // same bytes, but every store instruction of a warp writes 1 KB of CONTIGUOUS memory (wrong layout)
+                  const size_t slab = ((size_t)it * prm.njobs + j) * 128 * COUT + (size_t)((warp - kEpiWarp0) * (HALF / 16) + q) * 512 + lane * 16;
+                  st_global_v8(prm.out_hi + slab, h + 8 * q);
+                  if (!FAST) st_global_v8(prm.out_lo + slab, l + 8 * q);
+                } else
                 if (prm.dbg & 128) { st_global_2xv4(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_2xv4(prm.out_lo + ooff + 16 * q, l + 8 * q); }
                 else if (prm.dbg & 256) { st_global_v8_cs(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_v8_cs(prm.out_lo + ooff + 16 * q, l + 8 * q); }
                 else {

@@ -16,8 +16,9 @@ protobufs, the data file holds the raw little-endian tensors.  What is implement
 
 STATUS: this container has neither TensorFlow nor a checkpoint of the reference, so the reader is exercised against
 files produced by an independently written writer of the same layout (tests/tf_bundle_writer.py), not against
-TensorFlow's own output.  Compressed (snappy) blocks, sliced or sharded tensors and non-float dtypes other than the ones
-listed in _DTYPES are rejected with an error instead of being guessed at.
+TensorFlow's own output.  Snappy-compressed table blocks (LevelDB block type 1; TensorFlow's own writer leaves them
+uncompressed) and checkpoints sharded over several `.data-NNNNN-of-MMMMM` files are read; sliced tensors and dtypes other
+than the ones listed in _DTYPES are rejected with an error instead of being guessed at.
 """
 from __future__ import annotations
 
@@ -128,17 +129,54 @@ def _block_handle(buf: bytes, pos: int):
     return off, size, pos
 
 
+def snappy_uncompress(buf: bytes) -> bytes:
+    """Raw Snappy block format (the compression LevelDB tables use): varint uncompressed length, then literal and copy
+    elements.  tag & 3: 0 literal (length - 1 in the upper six bits, 60..63 = that many - 59 extra length bytes),
+    1 copy with an 11-bit offset (length 4..11), 2 copy with a 16-bit offset, 3 copy with a 32-bit offset (length 1..64)."""
+    n, pos = _varint(buf, 0)
+    out = bytearray()
+    while pos < len(buf):
+        tag = buf[pos]; pos += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                extra = ln - 59
+                ln = int.from_bytes(buf[pos:pos + extra], "little"); pos += extra
+            ln += 1
+            if pos + ln > len(buf):
+                raise ValueError("snappy: literal runs past the end of the block")
+            out += buf[pos:pos + ln]; pos += ln
+            continue
+        if kind == 1:
+            ln = ((tag >> 2) & 7) + 4
+            offset = ((tag >> 5) << 8) | buf[pos]; pos += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            offset = buf[pos] | (buf[pos + 1] << 8); pos += 2
+        else:
+            ln = (tag >> 2) + 1
+            offset = int.from_bytes(buf[pos:pos + 4], "little"); pos += 4
+        if offset == 0 or offset > len(out):
+            raise ValueError("snappy: copy offset outside the data written so far")
+        for _ in range(ln):                      # byte by byte: copies may overlap their own output (run-length encoding)
+            out.append(out[-offset])
+    if len(out) != n:
+        raise ValueError(f"snappy: block expands to {len(out)} bytes, header says {n}")
+    return bytes(out)
+
+
 def _read_block(data: bytes, off: int, size: int, verify: bool) -> bytes:
     body, trailer = data[off:off + size], data[off + size:off + size + 5]
     if len(body) != size or len(trailer) != 5:
         raise ValueError("block handle points outside the index file")
-    if trailer[0] != 0:
-        raise ValueError("compressed index blocks are not supported (type %d)" % trailer[0])
-    if verify:
+    if trailer[0] not in (0, 1):
+        raise ValueError("unknown table block type %d (0 = raw, 1 = snappy)" % trailer[0])
+    if verify:                                   # the checksum covers the stored (possibly compressed) bytes + type
         want = struct.unpack("<I", trailer[1:])[0]
         if mask_crc(crc32c(body + trailer[:1])) != want:
             raise ValueError("index block checksum mismatch")
-    return body
+    return snappy_uncompress(body) if trailer[0] == 1 else body
 
 
 def _block_entries(block: bytes):
@@ -181,19 +219,24 @@ def read_bundle(prefix: str, verify: bool = True) -> dict:
             num_shards = val
         elif field == 2 and val != 0:
             raise ValueError("big-endian checkpoints are not supported")
-    if num_shards != 1:
-        raise ValueError(f"checkpoint has {num_shards} shards; only single-shard checkpoints are supported")
-    data_path = f"{prefix}.data-00000-of-00001"
+    if num_shards < 1:
+        raise ValueError(f"checkpoint header names {num_shards} shards")
+    files = {}
     out = {}
-    with open(data_path, "rb") as f:
+    try:
         for key, value in index.items():
             if key == "":
                 continue
             dtype, shape, shard, offset, size, crc = _parse_entry(value)
             if dtype == 7:                                   # DT_STRING: _CHECKPOINTABLE_OBJECT_GRAPH
                 continue
-            if dtype not in _DTYPES or shard != 0:
-                raise ValueError(f"{key}: unsupported dtype {dtype} or shard {shard}")
+            if dtype not in _DTYPES:
+                raise ValueError(f"{key}: unsupported dtype {dtype}")
+            if not 0 <= shard < num_shards:
+                raise ValueError(f"{key}: shard {shard} of a checkpoint with {num_shards} shards")
+            if shard not in files:
+                files[shard] = open(f"{prefix}.data-{shard:05d}-of-{num_shards:05d}", "rb")
+            f = files[shard]
             f.seek(offset)
             raw = f.read(size)
             n = int(np.prod(shape, dtype=np.int64)) if shape else 1
@@ -202,6 +245,9 @@ def read_bundle(prefix: str, verify: bool = True) -> dict:
             if verify and crc is not None and mask_crc(crc32c(raw)) != crc:
                 raise ValueError(f"{key}: tensor checksum mismatch")
             out[key] = np.frombuffer(raw, dtype=np.dtype(_DTYPES[dtype]).newbyteorder("<")).reshape(shape).copy()
+    finally:
+        for f in files.values():
+            f.close()
     return out
 
 

@@ -233,6 +233,39 @@ def test_tensorflow_checkpoint_reader(nn, tmp_path):
     assert tfbundle.mask_crc(tfbundle.crc32c(b"123456789")) == (((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF
 
 
+def test_tensorflow_checkpoint_reader_snappy_and_shards(tmp_path):
+    """The table blocks of a bundle index may be Snappy-compressed (LevelDB block type 1) and the tensors may be spread over
+    several `.data-NNNNN-of-MMMMM` files: both are read; the Snappy decoder is also checked on its own element kinds
+    (long literals, 1- and 2-byte-offset copies, overlapping copies) and on malformed input."""
+    from tf_bundle_writer import snappy_compress, write_bundle
+    from neural_network_image_compression_b200 import tfbundle, weights as Wt
+    rng = np.random.default_rng(5)
+    for blob in (b"", b"a", b"abcd" * 5000, bytes(rng.integers(0, 4, size=70000, dtype=np.uint8)), bytes(rng.integers(0, 256, size=300, dtype=np.uint8)),
+                 b"x" * 100000, (b"conv1/kernel/.ATTRIBUTES/VARIABLE_VALUE" + bytes(range(40))) * 60):
+        packed = snappy_compress(blob)
+        assert tfbundle.snappy_uncompress(packed) == blob
+        if len(blob) > 1000:
+            assert len(packed) < len(blob)
+    assert tfbundle.snappy_uncompress(bytes([5, 0 << 2, ord("a"), 2 | (3 << 2), 1, 0])) == b"aaaaa"     # overlapping copy = run
+    for bad in (bytes([4, 2 | (3 << 2), 9, 0]), bytes([9, 0 << 2, ord("a")]), bytes([3, 8 << 2, ord("a")])):
+        with pytest.raises(ValueError, match="snappy"):
+            tfbundle.snappy_uncompress(bad)
+    w = Wt.glorot_uniform("decoder", 9, 1.1, 0.05)
+    names = [layer[0] for layer in Wt.layers_of("decoder")]
+    tensors = {f"{n}/{v}/.ATTRIBUTES/VARIABLE_VALUE": w[f"{n}/{v}"] for n in names for v in ("kernel", "bias")}
+    for shards, snappy in ((1, True), (3, False), (2, True)):
+        prefix = str(tmp_path / f"dec_{shards}_{int(snappy)}Y")
+        write_bundle(prefix, tensors, block_bytes=150, num_shards=shards, snappy=snappy)
+        assert os.path.exists(f"{prefix}.data-{shards - 1:05d}-of-{shards:05d}")
+        got = tfbundle.keras_weights(prefix, names)
+        for k in w:
+            assert np.array_equal(got[k], w[k]), (shards, snappy, k)
+    raw = bytearray(open(prefix + ".index", "rb").read()); raw[30] ^= 0x10
+    open(prefix + ".index", "wb").write(raw)
+    with pytest.raises(ValueError):
+        tfbundle.read_index(prefix + ".index")
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` needs no GPU: exactly one JSON line on stdout with the contract's keys."""
     import json
