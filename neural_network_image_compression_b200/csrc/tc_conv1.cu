@@ -157,9 +157,12 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     // aligned words that cover its 57 bytes.  Loads are unconditional from an always-valid (clamped) address, so all of
     // them are in flight together; rows / columns outside the image are zeroed at conversion (= TF SAME padding).  The
     // words of item k+1 are requested before item k is built, so their latency hides behind the im2col work.
-    const uintptr_t rgb0 = reinterpret_cast<uintptr_t>(prm.rgb);
+    const uintptr_t rgb0 = reinterpret_cast<uintptr_t>(prm.rgb), rgb_end = rgb0 + (size_t)N * H * W * 3;
     const uintptr_t buf_lo = rgb0 & ~(uintptr_t)3;
-    const uintptr_t buf_hi = ((rgb0 + (size_t)N * H * W * 3 + 3) & ~(uintptr_t)3) - 4;   // last aligned word that holds image bytes
+    const uintptr_t buf_hi = ((rgb_end + 3) & ~(uintptr_t)3) - 4;          // last aligned word that holds image bytes
+    // the first / last word may straddle the ends of the caller's buffer (a batch that does not start or end on a 4-byte
+    // boundary): those two words are assembled from in-range byte loads, every other word is one aligned 32-bit load
+    const uintptr_t full_lo = (rgb0 + 3) & ~(uintptr_t)3, full_hi = (rgb_end & ~(uintptr_t)3) - 4;
     uint32_t rawreg[RAW_PER];
     auto load_raw = [&](const ItemIter& t) {
       const int iy0 = t.ty * kTileRows * 2 - prm.pad_t, ix0 = t.tx * kTileCols * 2 - prm.pad_l;
@@ -172,7 +175,17 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         const uintptr_t row0 = rgb0 + (((ptrdiff_t)t.n * H + iy) * W + ix0) * 3;
         uintptr_t a = (row0 & ~(uintptr_t)3) + 4 * wd;
         a = a < buf_lo ? buf_lo : (a > buf_hi ? buf_hi : a);
-        rawreg[q] = (q < RAW_PER - 1 || i < RAW_WORDS) ? __ldg(reinterpret_cast<const uint32_t*>(a)) : 0u;
+        uint32_t v = 0u;
+        if (q < RAW_PER - 1 || i < RAW_WORDS) {
+          if (a >= full_lo && a <= full_hi) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(a));
+          } else {
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if (a + bb >= rgb0 && a + bb < rgb_end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(a + bb)) << (8 * bb);
+          }
+        }
+        rawreg[q] = v;
       }
     };
     int j_local = 0;                                       // this group's item counter

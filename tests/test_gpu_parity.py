@@ -769,3 +769,22 @@ def test_graph_codec_matches_direct_calls(nn, codec_factory):
         enc(x, out=lat); dec(lat, out=rgb)
     after = enc.handle.lib.nnic_tensor_map_encodes(enc.handle.h) + dec.handle.lib.nnic_tensor_map_encodes(dec.handle.h)
     assert after == before
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 9, 7), (3, 40, 56), (1, 64, 96)])
+def test_encoder_input_at_any_byte_alignment(nn, codec_factory, shape):
+    """conv1 fetches the RGB patch with aligned 32-bit loads and extracts the bytes in shared memory: an input tensor that
+    starts at any byte offset (a slice of a larger uint8 buffer) and ends flush with its allocation must give the bytes of
+    the aligned tensor -- the words that straddle the ends of the buffer are assembled from in-range byte loads."""
+    import torch
+    enc, _ = codec_factory("spread", "tc_split")
+    n, hh, ww = shape
+    img = synthetic_images(n, hh, ww, seed=hh + 3)
+    want = enc(img)
+    count = img.size
+    for off in (1, 2, 3, 5):
+        flat = torch.zeros(count + off, dtype=torch.uint8, device="cuda")      # the view ends exactly at the allocation's last byte
+        flat[off:] = torch.from_numpy(img.reshape(-1)).cuda()
+        x = flat[off:].view(n, hh, ww, 3)
+        assert x.data_ptr() % 4 == off % 4
+        assert np.array_equal(enc(x).cpu().numpy(), want), (shape, off)
