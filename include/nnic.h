@@ -218,6 +218,10 @@ int nnic_profile_collect(nnic_t* h, float* ms_per_kernel, int* launches_per_kern
  * memory as fp32 [3*nb,H,W,C].  out == NULL returns the element count. */
 void nnic_colour_constants(float* k9, float* kinv9, float* off3);
 long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity);
+/* The tensor-core layers keep activations as two fp16 planes of v*16, which saturate at |v| > 4094 where the fp32
+ * reference would carry on.  nnic_debug_saturated counts the saturated values in the activations of the most recent
+ * encode and decode micro-batch (synchronises the device): 0 = the representation was exact to its ~22 bits. */
+long long nnic_debug_saturated(nnic_t* h);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -53,6 +53,7 @@ SYMBOLS = (
     ("nnic_profile_collect", C.c_int, (_vp, _vp, _vp, C.c_int)),
     ("nnic_colour_constants", None, (_vp, _vp, _vp)),
     ("nnic_debug_fetch", C.c_longlong, (_vp, C.c_int, _vp, C.c_longlong)),
+    ("nnic_debug_saturated", C.c_longlong, (_vp,)),
 )
 
 # include/nnic.h enum nnic_kernel_id
@@ -166,6 +167,13 @@ class Handle:
         if rc < 0:
             self.check(rc, "nnic_profile_collect")
         return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(len(KERNEL_NAMES)) if cnt[i]}
+
+    def saturated_activations(self) -> int:
+        """Values of the last encode / decode micro-batch that hit the fp16 limit of the split representation (|v| > 4094)."""
+        n = int(self.lib.nnic_debug_saturated(self.h))
+        if n < 0:
+            self.check(n, "nnic_debug_saturated")
+        return n
 
     def debug_fetch(self, slot: int) -> np.ndarray:
         n = self.lib.nnic_debug_fetch(self.h, slot, None, 0)

@@ -65,6 +65,9 @@ cudaError_t launch_f32_to_split(const float* in, size_t count, __half* out_hi, _
 cudaError_t launch_quantise(const float* planes, int N, int lh, int lw, uint8_t* latent, float* prequant,
                             cudaStream_t stream);
 
+// adds to *out the number of values of a split-fp16 hi plane at the saturation limit (|v * 16| >= 65504)
+cudaError_t launch_count_saturated(const __half* hi, size_t n, unsigned long long* out, int num_sms, cudaStream_t stream);
+
 // ---- rate ---------------------------------------------------------------------------------------
 // hist u32 [N][3][256] must be zeroed by the caller (launch_hist adds into it).
 cudaError_t launch_hist(const uint8_t* latent, int N, size_t pixels_per_image, uint32_t* hist, int num_sms, int variant,

@@ -144,8 +144,8 @@ struct nnic_handle {
   int prof_id = 0;
 
   // debug: tensors of the most recent encode/decode micro-batch
-  struct Dbg { const __half* hi; const __half* lo; const float* f32; size_t count; };
-  Dbg dbg[8] = {};
+  struct Dbg { const __half* hi; const __half* lo; const float* f32; size_t count; size_t stored; };
+  Dbg dbg[9] = {};
 };
 
 namespace {
@@ -551,7 +551,7 @@ inline size_t act_bytes(bool split, size_t P, size_t H, size_t W, size_t C) {
   return split ? 2 * pad1k(P * H * W * C * 2) : pad1k(P * H * W * C * 4);
 }
 void record_dbg(nnic_t* h, int slot, const Act& a, int P) {
-  h->dbg[slot] = {a.hi, a.lo, a.f32, (size_t)P * a.H * a.W * a.C};
+  h->dbg[slot] = {a.hi, a.lo, a.f32, (size_t)P * a.H * a.W * a.C, (size_t)P * a.Hs * a.Ws * a.C};
 }
 
 // A tensor-core kernel whose barrier wait timed out writes a code into mapped host memory and traps.  The flag is read
@@ -810,7 +810,7 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   } else {
     CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
   }
-  record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
+  record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P); record_dbg(h, 8, d4, P);
   h->arena_used = base_used;
   return 0;
 }
@@ -1518,6 +1518,29 @@ long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity) 
     for (size_t i = 0; i < d.count; ++i) out[i] = (__half2float(hi[i]) + __half2float(lo[i])) * ACT_INV_SCALE;
   }
   return (long long)d.count;
+}
+
+// The split-fp16 activation planes hold v * 16 and saturate at the fp16 maximum (|v| > 4094), where the fp32 reference would
+// carry on: a trained codec stays far below that (activations of O(1)), but nothing in the kernels reports it.  This debug
+// call counts the saturated values in the activations of the most recent encode (conv1 .. conv4) and decode (dconv1 .. dconv7)
+// micro-batch of the handle; 0 means the split representation was exact to its 22 bits everywhere.
+long long nnic_debug_saturated(nnic_t* h) {
+  if (!h) return NNIC_ERR_INVALID_ARG;
+  DeviceGuard g(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "sync failed");
+  unsigned long long* d_cnt = nullptr;
+  if (cudaMalloc(&d_cnt, 8) != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "cudaMalloc failed");
+  cudaMemset(d_cnt, 0, 8);
+  for (int s = 0; s < 9; ++s) {
+    const nnic_handle::Dbg& d = h->dbg[s];
+    if (!d.hi || !d.stored || (s == 4 && h->int_latent && !h->decode_fp16)) continue;   // slot 4 may hold the integer symbols
+    if (launch_count_saturated(d.hi, d.stored, d_cnt, h->num_sms, nullptr) != cudaSuccess) { cudaFree(d_cnt); return fail(h, NNIC_ERR_CUDA, "launch failed"); }
+  }
+  unsigned long long cnt = 0;
+  const cudaError_t e = cudaMemcpy(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_cnt);
+  if (e != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "copy failed");
+  return (long long)cnt;
 }
 
 }  // extern "C"

@@ -515,6 +515,22 @@ cudaError_t launch_f32_to_split(const float* in, size_t count, __half* out_hi, _
   return cudaGetLastError();
 }
 
+// values of a split-fp16 hi plane that sit at the saturation limit of the representation (nnic_debug_saturated)
+__global__ void __launch_bounds__(256) k_count_saturated(const __half* __restrict__ hi, size_t n, unsigned long long* __restrict__ out) {
+  unsigned int c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c += (__half_as_ushort(hi[i]) & 0x7fffu) >= 0x7bffu;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+cudaError_t launch_count_saturated(const __half* hi, size_t n, unsigned long long* out, int num_sms, cudaStream_t stream) {
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)num_sms * 16;
+  k_count_saturated<<<(unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)), 256, 0, stream>>>(hi, n, out);
+  return cudaGetLastError();
+}
+
 // Reference: Encoder.__call__ lines 45,47: concat(axis=3) in plane order, np.round(e*255).astype(uint8).
 __global__ void __launch_bounds__(256) k_quantise(const float* __restrict__ planes, int N, size_t pix,
                                                   uint8_t* __restrict__ latent, float* __restrict__ prequant) {

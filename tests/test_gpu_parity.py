@@ -788,3 +788,19 @@ def test_encoder_input_at_any_byte_alignment(nn, codec_factory, shape):
         x = flat[off:].view(n, hh, ww, 3)
         assert x.data_ptr() % 4 == off % 4
         assert np.array_equal(enc(x).cpu().numpy(), want), (shape, off)
+
+
+def test_saturation_of_the_split_representation_is_detectable(nn, codec_factory):
+    """activations are stored as fp16 pairs of v*16 and saturate at |v| > 4094, silently.  With the test weight sets
+    nothing saturates; with one kernel blown up by 1e5 the debug counter reports it (and the fp32 FFMA arithmetic differs)."""
+    img = synthetic_images(2, 64, 96, seed=17)
+    enc, dec = codec_factory("spread", "tc_split")
+    lat = enc(img); dec(lat)
+    assert enc.handle.saturated_activations() == 0 and dec.handle.saturated_activations() == 0
+    eY, eC, _dY, _dC = make_weights("spread")
+    big = nn.Encoder(0)
+    for i, w in enumerate((eY, eC)):
+        w2 = {k: (v * np.float32(1.0e5) if k.startswith("conv2/kernel") else v) for k, v in w.items()}
+        big.set_weights(i, w2)
+    big(img)
+    assert big.handle.saturated_activations() > 0
