@@ -377,6 +377,11 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (valid) {
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {
+                if (prm.dbg & 1024) {            // same bytes and store pattern, but folded into a 4 MB window: the lines are rewritten in L2 and hardly reach DRAM
+                  const size_t w_ = (ooff + 16 * q) & (((size_t)1 << 20) - 1);
+                  st_global_v8(prm.out_hi + w_, h + 8 * q);
+                  if (!FAST) st_global_v8(prm.out_lo + w_, l + 8 * q);
+                } else
                 if (prm.dbg & 512) {             // same bytes, but every store instruction of a warp writes 1 KB of CONTIGUOUS memory (wrong layout)
                   const size_t slab = ((size_t)it * prm.njobs + j) * 128 * COUT + (size_t)((warp - kEpiWarp0) * (HALF / 16) + q) * 512 + lane * 16;
                   st_global_v8(prm.out_hi + slab, h + 8 * q);
