@@ -63,6 +63,13 @@ struct PCfg {
 };
 
 // role timers (profiles/r1_tcprof_*.log) are compiled in with -DNNIC_TC_TIMERS; they cost a few hundred cycles per tile
+// Development switches (NNIC_TC_DBG, kernels.h) exist only in the -DNNIC_TC_DEVELOP build (libnnic_dev.so, `make dev`), which
+// tools/dbg_sweep.sh loads through NNIC_LIB; in the product library DBG() is a compile-time false and the branches vanish.
+#ifdef NNIC_TC_DEVELOP
+#define DBG(bit) ((prm.dbg & (bit)) != 0)
+#else
+#define DBG(bit) false
+#endif
 #ifdef NNIC_TC_TIMERS
 #define TICK() ((long long)clock64())
 #else
@@ -147,7 +154,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_wait(&patch_empty[pb], pphase ^ 1, wc, 1);
         if (elect_one()) {
           uint8_t* pbuf = patch_base + pb * SET_BYTES;
-          if ((prm.dbg & 16) || ((prm.dbg & 64) && it >= (int)blockIdx.x + NSETS * (int)gridDim.x)) {   // 64: only the first NSETS items load
+          if (DBG(16) || (DBG(64) && it >= (int)blockIdx.x + NSETS * (int)gridDim.x)) {   // 64: only the first NSETS items load
             mbar_arrive(&patch_full[pb]);
           } else {
             mbar_expect_tx(&patch_full[pb], (FAST || AHI) ? PATCH_TX : 2 * PATCH_TX);
@@ -184,7 +191,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           { long long t0 = TICK(); mbar_wait(&w_empty[ws], wphase ^ 1, wc, 2); tw_w += TICK() - t0; }
           if (elect_one()) {
             uint8_t* wb = w_base + ws * W_SLOT;
-            if ((prm.dbg & 4) || ((prm.dbg & 32) && w_loaded >= WSLOTS)) {   // 32: only the first ring pass loads (real data, no refills)
+            if (DBG(4) || (DBG(32) && w_loaded >= WSLOTS)) {   // 32: only the first ring pass loads (real data, no refills)
               mbar_arrive(&w_full[ws]);
             } else {
               mbar_expect_tx(&w_full[ws], FAST ? W_TILE : W_SLOT);
@@ -250,7 +257,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               if (k < ntaps) {
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
                 tc_fence_after();
-                if (active && !(prm.dbg & 1)) {
+                if (active && !DBG(1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
                   const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
                   const uint64_t w_hl = make_desc_sbo(w_u32 + w * W_SLOT, C::W_SBO, C::LAYOUT);   // W_hi followed by W_lo
@@ -312,7 +319,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // accesses (one full 32-byte sector per thread and instruction)
         const int oY = tY0 + lg * 4 + (lane >> 3), oX = tX0 + (lane & 7);
         const int ooy = oY * prm.out_stride + prm.jobs[j].out_oy, oox = oX * prm.out_stride + prm.jobs[j].out_ox;
-        const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo && !(prm.dbg & 2);
+        const bool valid = oY < prm.Hp && oX < prm.Wp && ooy < prm.Ho && oox < prm.Wo && !DBG(2);
         const size_t ooff = (((size_t)p * prm.Hs + ooy) * prm.Ws + oox) * COUT + ch0;
         // residual: loaded now so that its latency hides behind the MMAs
         uint32_t res_h[HALF / 2], res_l[HALF / 2];
@@ -336,7 +343,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
           uint32_t vm[HALF], vc[HALF];
-          if (prm.dbg & 8) {
+          if (DBG(8)) {
 #pragma unroll
             for (int i = 0; i < HALF; ++i) { vm[i] = 0; vc[i] = 0; }
           } else if (HALF == 32) { tmem_ld32_nowait(taddr, vm); if (!FAST) tmem_ld32_nowait(taddr + COUT, vc); }
@@ -377,18 +384,18 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (valid) {
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {
-                if (prm.dbg & 1024) {            // same bytes and store pattern, but folded into a 4 MB window: the lines are rewritten in L2 and hardly reach DRAM
+                if (DBG(1024)) {            // same bytes and store pattern, but folded into a 4 MB window: the lines are rewritten in L2 and hardly reach DRAM
                   const size_t w_ = (ooff + 16 * q) & (((size_t)1 << 20) - 1);
                   st_global_v8(prm.out_hi + w_, h + 8 * q);
                   if (!FAST) st_global_v8(prm.out_lo + w_, l + 8 * q);
                 } else
-                if (prm.dbg & 512) {             // same bytes, but every store instruction of a warp writes 1 KB of CONTIGUOUS memory (wrong layout)
+                if (DBG(512)) {             // same bytes, but every store instruction of a warp writes 1 KB of CONTIGUOUS memory (wrong layout)
                   const size_t slab = ((size_t)it * prm.njobs + j) * 128 * COUT + (size_t)((warp - kEpiWarp0) * (HALF / 16) + q) * 512 + lane * 16;
                   st_global_v8(prm.out_hi + slab, h + 8 * q);
                   if (!FAST) st_global_v8(prm.out_lo + slab, l + 8 * q);
                 } else
-                if (prm.dbg & 128) { st_global_2xv4(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_2xv4(prm.out_lo + ooff + 16 * q, l + 8 * q); }
-                else if (prm.dbg & 256) { st_global_v8_cs(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_v8_cs(prm.out_lo + ooff + 16 * q, l + 8 * q); }
+                if (DBG(128)) { st_global_2xv4(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_2xv4(prm.out_lo + ooff + 16 * q, l + 8 * q); }
+                else if (DBG(256)) { st_global_v8_cs(prm.out_hi + ooff + 16 * q, h + 8 * q); if (!FAST) st_global_v8_cs(prm.out_lo + ooff + 16 * q, l + 8 * q); }
                 else {
                 st_global_v8(prm.out_hi + ooff + 16 * q, h + 8 * q);
                 if (!FAST) st_global_v8(prm.out_lo + ooff + 16 * q, l + 8 * q);
