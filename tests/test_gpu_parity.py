@@ -804,3 +804,38 @@ def test_saturation_of_the_split_representation_is_detectable(nn, codec_factory)
         big.set_weights(i, w2)
     big(img)
     assert big.handle.saturated_activations() > 0
+
+
+def test_heavy_tailed_weights_against_oracle(nn):
+    """Trained networks do not look like a glorot draw: per-channel gains that span two orders of magnitude and biases of
+    +-0.5 exercise the power-of-two weight scaling (max |w| just below 32768) and the hi/lo split of small weights next to
+    large ones.  Symbols and reconstruction bytes against the fp64 oracle, ties only."""
+    from neural_network_image_compression_b200 import weights as Wt
+    rng = np.random.default_rng(123)
+
+    def heavy(kind, seed):
+        w = Wt.glorot_uniform(kind, seed, 1.0, 0.0)
+        for name, _k, _s, _cin, cout in Wt.layers_of(kind):
+            gains = np.exp(rng.uniform(np.log(0.15), np.log(6.0), size=cout)).astype(np.float32)
+            gains /= np.float32(np.sqrt(np.mean(gains ** 2)))                 # keep the layer's overall scale
+            kern = w[name + "/kernel"]
+            w[name + "/kernel"] = (kern * gains if kind == "encoder" else kern * gains[None, None, :, None]).astype(np.float32)
+            w[name + "/bias"] = rng.uniform(-0.5, 0.5, size=cout).astype(np.float32) * np.float32(0.2)
+        return w
+    eY, eC, dY, dC = heavy("encoder", 31), heavy("encoder", 32), heavy("decoder", 33), heavy("decoder", 34)
+    enc, dec = nn.Encoder(0), nn.Decoder(0)
+    enc.set_weights(0, eY); enc.set_weights(1, eC); dec.set_weights(0, dY); dec.set_weights(1, dC)
+    img = synthetic_images(3, 128, 192, seed=55)
+    sym, pre = enc(img, return_prequant=True)
+    pre64 = O.encode_prequant(img, eY, eC, "f64")
+    sym64 = O.quantise(pre64)
+    tie = np.abs(pre64 * 255.0 - np.floor(pre64 * 255.0) - 0.5)
+    lam = SYMBOL_MISMATCH_LIMIT * sym.size
+    check_symbols(sym, sym64, tie, min_allow=int(lam + 4 * np.sqrt(lam) + 2))
+    assert 0.02 < (sym64 > 0).mean() and np.abs(pre - pre64).max() < 5e-5
+    d64 = O.decode_prequant(sym64, dY, dC, "f64")
+    rec64 = np.round(d64 * 255.0).astype(np.uint8)
+    tie_r = np.abs(d64 * 255.0 - np.floor(d64 * 255.0) - 0.5)
+    lam = SYMBOL_MISMATCH_LIMIT * rec64.size
+    check_symbols(dec(sym64), rec64, tie_r, min_allow=int(lam + 4 * np.sqrt(lam) + 2))
+    assert enc.handle.saturated_activations() == 0 and dec.handle.saturated_activations() == 0
