@@ -18,8 +18,8 @@
 //     slots 5, 11, 17, 23, 29, 30, 31);
 //   * four builder groups (two warps each) work on different items; a group's first warp issues the MMAs of its three
 //     planes (2 k-steps x [A_hi x [W_hi|W_lo], A_lo x W_hi]) into TMEM slots [main 32 | corr 32];
-//   * eight epilogue warps (TMEM lane group x channel half) add bias, apply leaky_relu, split to fp16 hi/lo and write each
-//     pixel's 16 channels with one 256-bit store per plane.
+//   * eight epilogue warps in two teams (a team = four TMEM lane groups, alternate tiles; a thread owns the 32 channels of one
+//     pixel) add bias, apply leaky_relu, split to fp16 hi/lo and write two 256-bit stores per plane.
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -30,12 +30,14 @@ namespace {
 using namespace tc;
 
 constexpr int kBuilderWarps = 8, kEpiWarps = 8;
+constexpr int kTeams = kEpiWarps / 4;                 // epilogue teams (one warp per TMEM lane group each) on alternate tiles
 constexpr int kEpiWarp0 = kBuilderWarps;              // warps 0-7 builders (the first warp of a group also issues its MMAs), 8-15 epilogue
 constexpr int kThreads = (kBuilderWarps + kEpiWarps) * 32;       // 512: four warps per scheduler, 128 registers per thread
 constexpr int CO = 32;                                // output channels
 constexpr int PH = 2 * kTileRows + 3, PW = 2 * kTileCols + 3;    // 35 x 19 input pixels
-constexpr int PPITCH = 24;                            // fp16 per row of a converted plane (19 used + zero slot 19; 12 words:
-                                                      // the 4 x 8 output pixels a warp builds read 32 distinct banks)
+constexpr int PPITCH = 24;                            // fp16 per row of a converted plane (19 used + zero slots 19-23; 12 words =
+                                                      // 48 bytes: the 64-bit loads of a half-warp (4 tile rows x 4 column pairs)
+                                                      // fall into 32 distinct banks)
 constexpr int PPLANE = PH * PPITCH;                   // fp16 per (colour plane, half)
 constexpr int RAW_PITCH = 64;                         // bytes per staged raw row: 19 pixels * 3 bytes + up to 3 bytes of misalignment
 constexpr int A_TILE = kTileM * 64;                   // 8 KB: 128 rows x 32 fp16
@@ -55,7 +57,8 @@ constexpr int BAR_OFF = (W_OFF + 2 * W_SET + 1023) / 1024 * 1024;
 constexpr int SMEM_BYTES = BAR_OFF + 512 + 2 * CO * 4 + 1024;
 constexpr int RAW_WORDS = PH * (RAW_PITCH / 4);       // 560 words per item
 constexpr int RAW_PER = (RAW_WORDS + GTHREADS - 1) / GTHREADS;   // 9 per thread
-constexpr int PER = (PH * PW + GTHREADS - 1) / GTHREADS;         // 11 pixels per thread
+constexpr int PPAIRS_ROW = (PW + 1) / 2;                         // 10 column pairs per patch row
+constexpr int PPER = (PH * PPAIRS_ROW + GTHREADS - 1) / GTHREADS;   // 6 pixel pairs per thread
 
 // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row m lives at chunk j ^ ((m >> 1) & 3)
 __device__ __forceinline__ uint32_t sw64(int m, int j) { return (uint32_t)(m * 64 + ((j ^ ((m >> 1) & 3)) << 4)); }
@@ -114,7 +117,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-    for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], kEpiWarps); }
+    for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 2 * CO; i += kThreads) bias_s[i] = prm.bias[i] * ACT_SCALE;   // the epilogue works on scaled values
@@ -143,13 +146,14 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     uint8_t* gbase = smem + PATCH_OFF + g * GROUP_BYTES;
     __half* planes_s = reinterpret_cast<__half*>(gbase);                  // [3 colour planes][hi, lo][PH][PPITCH]
     uint8_t* raw_s = gbase + PATCH_BYTES;                                 // [PH][RAW_PITCH] staged RGB bytes
-    // the patch pixels this thread converts: i = gt + 64 q -> (row, column); fixed for the whole kernel
-    int16_t prc[PER];                                      // row | column << 8
+    // the patch pixel PAIRS this thread converts: i = gt + 64 q -> (row, column pair); fixed for the whole kernel.  A row has
+    // ten pairs: columns (0,1) .. (18,19), column 19 being the zero slot of the K layout
+    int16_t prc[PPER];                                     // row | column pair << 8
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
+    for (int q = 0; q < PPER; ++q) {
       const int i = gt + q * GTHREADS;
-      const int pr = i / PW, pc = i - pr * PW;
-      prc[q] = (int16_t)(pr | (pc << 8));
+      const int pr = i / PPAIRS_ROW, pcp = i - pr * PPAIRS_ROW;
+      prc[q] = (int16_t)(pr | (pcp << 8));
     }
     ItemIter it;
     it.init(blockIdx.x + g * gridDim.x, GROUPS * gridDim.x, tiles_x, tiles_y);
@@ -203,41 +207,51 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         }
         group_barrier(g);
       }
-      // ---- conversion: every pixel normalised once, projected onto Y, Cb, Cr, split once per plane ----
+      // ---- conversion: every pixel normalised once, projected onto Y, Cb, Cr, split once per plane; two neighbouring pixels
+      //      per step, so that their fp16 halves are stored as one 32-bit word per plane ----
       // byte address of patch pixel (0, 0); it may lie outside the buffer (padding), only its low two bits are used
-      const uintptr_t img0 = rgb0 + (((ptrdiff_t)n * H + iy0) * W + ix0) * 3;
+      const uint32_t img0_lo = (uint32_t)(rgb0 + (((ptrdiff_t)n * H + iy0) * W + ix0) * 3);
+      const uint32_t row_bytes = (uint32_t)W * 3u;
+      uint32_t* planes_w = reinterpret_cast<uint32_t*>(planes_s);
 #pragma unroll
-      for (int q = 0; q < PER; ++q) {
-        if (q < PER - 1 || gt + q * GTHREADS < PH * PW) {
-          const int pr = prc[q] & 0xff, pc = prc[q] >> 8;
-          const bool ok = interior || ((unsigned)(iy0 + pr) < (unsigned)H && (unsigned)(ix0 + pc) < (unsigned)W);
-          float v[3];
+      for (int q = 0; q < PPER; ++q) {
+        if (q < PPER - 1 || gt + q * GTHREADS < PH * PPAIRS_ROW) {
+          const int pr = prc[q] & 0xff, pc = 2 * (prc[q] >> 8);
+          const bool okr = interior || (unsigned)(iy0 + pr) < (unsigned)H;
+          const bool ok0 = okr && (interior || (unsigned)(ix0 + pc) < (unsigned)W);
+          const bool ok1 = okr && pc + 1 < PW && (interior || (unsigned)(ix0 + pc + 1) < (unsigned)W);
+          float v0[3], v1[3];
           if (IN_KIND == 0) {
             int iy = iy0 + pr;
             iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
             // the staged row starts at the aligned word below byte (iy, ix0); this pixel sits (row0 & 3) + 3 pc bytes in
             // (a clamped row or word holds other bytes, but only for pixels that are masked out below)
-            const uint32_t mis = (uint32_t)((img0 + (ptrdiff_t)(iy - iy0) * W * 3) & 3);
+            const uint32_t mis = (img0_lo + (uint32_t)(iy - iy0) * row_bytes) & 3u;
             const uint8_t* px = raw_s + pr * RAW_PITCH + mis + 3 * pc;
             // x.astype(float32)/255, then (t0*k0 + t1*k1) + t2*k2 with separate roundings, then + offset
-            const float r_ = div255(px[0]), g_ = div255(px[1]), b_ = div255(px[2]);
+            const float r0 = div255(px[0]), g0 = div255(px[1]), b0 = div255(px[2]);
+            const float r1 = div255(px[3]), g1 = div255(px[4]), b1 = div255(px[5]);
 #pragma unroll
-            for (int pl = 0; pl < 3; ++pl)
-              v[pl] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r_, prm.cc.k[pl][0]), __fmul_rn(g_, prm.cc.k[pl][1])),
-                                          __fmul_rn(b_, prm.cc.k[pl][2])), prm.cc.off[pl]);
+            for (int pl = 0; pl < 3; ++pl) {
+              v0[pl] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, prm.cc.k[pl][0]), __fmul_rn(g0, prm.cc.k[pl][1])),
+                                           __fmul_rn(b0, prm.cc.k[pl][2])), prm.cc.off[pl]);
+              v1[pl] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1, prm.cc.k[pl][0]), __fmul_rn(g1, prm.cc.k[pl][1])),
+                                           __fmul_rn(b1, prm.cc.k[pl][2])), prm.cc.off[pl]);
+            }
           } else {
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) {
-              const float* pf = ok ? prm.planes + (((size_t)(pl * N + n) * H + (iy0 + pr)) * W + (ix0 + pc)) : prm.planes;
-              v[pl] = *pf;
+              const float* pf = prm.planes + (((size_t)(pl * N + n) * H + (iy0 + pr)) * W + (ix0 + pc));
+              v0[pl] = ok0 ? pf[0] : 0.0f;
+              v1[pl] = ok1 ? pf[1] : 0.0f;
             }
           }
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
-            __half hi, lo;
-            split_f32(ok ? v[pl] : 0.0f, hi, lo);              // split once per input pixel; every tap that uses it copies the halves
-            planes_s[(pl * 2 + 0) * PPLANE + pr * PPITCH + pc] = hi;
-            planes_s[(pl * 2 + 1) * PPLANE + pr * PPITCH + pc] = lo;
+            uint32_t hi2, lo2;                   // split once per input pixel; every tap that uses it copies the halves
+            split2_f32(ok0 ? v0[pl] : 0.0f, ok1 ? v1[pl] : 0.0f, hi2, lo2);
+            planes_w[((pl * 2 + 0) * PPLANE + pr * PPITCH + pc) >> 1] = hi2;
+            planes_w[((pl * 2 + 1) * PPLANE + pr * PPITCH + pc) >> 1] = lo2;
           }
         }
       }
@@ -255,26 +269,34 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         uint8_t* a_lo = a_hi + A_TILE;
         const uint32_t* ph_w = reinterpret_cast<const uint32_t*>(planes_s + (pl * 2 + 0) * PPLANE);
         const uint32_t* pl_w = reinterpret_cast<const uint32_t*>(planes_s + (pl * 2 + 1) * PPLANE);
-#pragma unroll
-        for (int mm = 0; mm < 2; ++mm) {
-          const int m = gt + mm * GTHREADS;
-          const int r = m >> 3, c = m & 7;
-          // K slot 6 kh + s = input pixel (2r + kh, 2c + s): word w of kernel row kh is pixels 2c + 2w, 2c + 2w + 1
-          const int w0 = (2 * r) * (PPITCH / 2) + c;
-          uint32_t hw[16], lw[16];
+        {
+          // a thread builds the rows of two horizontally neighbouring output pixels (r, c) and (r, c + 1), c even: their
+          // kernel-row windows (input columns 2c .. 2c+5 and 2c+2 .. 2c+7) lie in 16 aligned bytes of the plane row, i.e. two
+          // 64-bit loads per (kernel row, half) serve both rows -- words 0-2 for the first, words 1-3 for the second.
+          // K slot 6 kh + s = input pixel (2r + kh, 2c + s)
+          const int r = gt >> 2, c = (gt & 3) * 2;
+          const int m = r * kTileCols + c;
+          const int w0 = (2 * r) * (PPITCH / 2) + c;                 // word index of input pixel (2r, 2c)
+          uint32_t hw[2][16], lw[2][16];
 #pragma unroll
           for (int kh = 0; kh < 5; ++kh) {
-#pragma unroll
-            for (int w_ = 0; w_ < 3; ++w_) {
-              hw[3 * kh + w_] = ph_w[w0 + kh * (PPITCH / 2) + w_];
-              lw[3 * kh + w_] = pl_w[w0 + kh * (PPITCH / 2) + w_];
-            }
+            const uint2 h01 = *reinterpret_cast<const uint2*>(ph_w + w0 + kh * (PPITCH / 2));
+            const uint2 h23 = *reinterpret_cast<const uint2*>(ph_w + w0 + kh * (PPITCH / 2) + 2);
+            const uint2 l01 = *reinterpret_cast<const uint2*>(pl_w + w0 + kh * (PPITCH / 2));
+            const uint2 l23 = *reinterpret_cast<const uint2*>(pl_w + w0 + kh * (PPITCH / 2) + 2);
+            hw[0][3 * kh] = h01.x; hw[0][3 * kh + 1] = h01.y; hw[0][3 * kh + 2] = h23.x;
+            hw[1][3 * kh] = h01.y; hw[1][3 * kh + 1] = h23.x; hw[1][3 * kh + 2] = h23.y;
+            lw[0][3 * kh] = l01.x; lw[0][3 * kh + 1] = l01.y; lw[0][3 * kh + 2] = l23.x;
+            lw[1][3 * kh] = l01.y; lw[1][3 * kh + 1] = l23.x; lw[1][3 * kh + 2] = l23.y;
           }
-          hw[15] = 0u; lw[15] = 0u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(a_hi + sw64(m, j)) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-            *reinterpret_cast<uint4*>(a_lo + sw64(m, j)) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+          for (int e = 0; e < 2; ++e) {
+            hw[e][15] = 0u; lw[e][15] = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(a_hi + sw64(m + e, j)) = make_uint4(hw[e][4 * j], hw[e][4 * j + 1], hw[e][4 * j + 2], hw[e][4 * j + 3]);
+              *reinterpret_cast<uint4*>(a_lo + sw64(m + e, j)) = make_uint4(lw[e][4 * j], lw[e][4 * j + 1], lw[e][4 * j + 2], lw[e][4 * j + 3]);
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to tcgen05.mma
@@ -303,51 +325,41 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     }
   } else {
     // ===================== epilogue warps =====================
-    // 8 warps: warp w reads TMEM lanes 32*(w%4)..+31 and 16 of the 32 channels
-    constexpr int HALF = CO / 2;
+    // Teams of four warps (one warp per TMEM lane group) share the (item, plane) tiles of the CTA's sequence; a thread owns
+    // ALL 32 channels of one pixel, so the per-tile bookkeeping (barrier wait, slot arithmetic, pixel address) is paid once
+    // per 32 values, and while one team waits for its TMEM loads the others compute.  A TMEM slot always belongs to the same
+    // team (slot % kTeams): every use of a slot is then drained in order by one team, so a parity wait can never be
+    // satisfied by the slot's previous-but-one use.
     const int ew = warp - kEpiWarp0;
     const int lg = warp & 3;                  // TMEM lane group
-    const int hf = ew >> 2;
-    const int ch0 = hf * HALF;
-    // The CTA's (item, plane) sequence in the order the epilogue drains it: item j (built by group j % GROUPS), planes 0..2.
-    struct Seq {
-      ItemIter it; int j, pl;
-      __device__ __forceinline__ int slot() const { return (j % GROUPS) * 2 + ((3 * (j / GROUPS) + pl) & 1); }
-      __device__ __forceinline__ uint32_t phase() const { return (uint32_t)((3 * (j / GROUPS) + pl) >> 1) & 1u; }
-      __device__ __forceinline__ void advance(int tx_, int ty_) { if (++pl == 3) { pl = 0; ++j; it.next(tx_, ty_); } }
-    };
-    Seq cur;
-    cur.it.init(blockIdx.x, gridDim.x, tiles_x, tiles_y); cur.j = 0; cur.pl = 0;
-    // Software-pipelined: the TMEM loads of tile t+1 are issued before the arithmetic of tile t, so the TMEM
-    // and barrier latencies overlap the bias / leaky / split / store work instead of adding to it.  The loop is
-    // unrolled by two so that the two register buffers swap roles without copies.
-    uint32_t am[HALF], ac[HALF], bm[HALF], bc[HALF];
-    auto issue_loads = [&](const Seq& s, uint32_t* vm, uint32_t* vc) {
-      const int slot = s.slot();
-      mbar_wait(&slot_full[slot], s.phase(), wc, 4);
+    const int team = ew >> 2;
+    const int m = lg * 32 + lane;
+    const int my = m >> 3, mx = m & 7;
+    ItemIter it;
+    it.init(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+    for (int j = 0; it.n < N; ++j, it.next(tiles_x, tiles_y)) {      // item j of the CTA, built by group j % GROUPS
+     for (int pl = 0; pl < 3; ++pl) {
+      const int lc = 3 * (j / GROUPS) + pl;    // the building group's (item, plane) counter
+      const int slot = (j % GROUPS) * 2 + (lc & 1);
+      if (slot % kTeams != team) continue;
+      mbar_wait(&slot_full[slot], (uint32_t)(lc >> 1) & 1u, wc, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS + ch0;
-      tmem_ld16_nowait(taddr, vm);
-      tmem_ld16_nowait(taddr + CO, vc);
-    };
-    auto release_slot = [&](const Seq& s) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + slot * SLOT_COLS;
+      uint32_t vm[CO], vc[CO];
+      tmem_ld32_nowait(taddr, vm);
+      tmem_ld32_nowait(taddr + CO, vc);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&slot_empty[s.slot()]);
-    };
-    const int m = lg * 32 + lane;
-    const int my = m >> 3, mx = m & 7;
-    // one tile: values are kept multiplied by ACT_SCALE (a power of two: bias add, leaky_relu and the hi/lo split
-    // commute with it bit for bit), which saves the scaling multiplies of the split
-    auto finish_tile = [&](const Seq& s, const uint32_t* vm, const uint32_t* vc) {
-      const int set = s.pl == 0 ? 0 : 1;
-      const int p = s.pl * N + s.it.n;
+      if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      // values are kept multiplied by ACT_SCALE (a power of two: bias add, leaky_relu and the hi/lo split commute with it
+      // bit for bit), which saves the scaling multiplies of the split
+      const int set = pl == 0 ? 0 : 1;
       const float inv16 = prm.inv_scale[set] * ACT_SCALE;
-      const float4* bs4 = reinterpret_cast<const float4*>(bias_s + set * CO + ch0);
-      uint32_t h[HALF / 2], l[HALF / 2];
+      const float4* bs4 = reinterpret_cast<const float4*>(bias_s + set * CO);
+      uint32_t h[CO / 2], l[CO / 2];
 #pragma unroll
-      for (int i = 0; i < HALF; i += 4) {
+      for (int i = 0; i < CO; i += 4) {
         const float4 b = bs4[i / 4];
         float v0 = fmaf(__fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])), inv16, b.x);
         float v1 = fmaf(__fadd_rn(__uint_as_float(vm[i + 1]), __uint_as_float(vc[i + 1])), inv16, b.y);
@@ -360,27 +372,16 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         split2_scaled(v0, v1, h[i / 2], l[i / 2]);
         split2_scaled(v2, v3, h[i / 2 + 1], l[i / 2 + 1]);
       }
-      // 16 channels = 32 bytes per fp16 plane: one 256-bit store each (a full sector per thread)
-      const int y = s.it.ty * kTileRows + my, x = s.it.tx * kTileCols + mx;
+      // 32 channels = 64 bytes per fp16 plane: two 256-bit stores each (two full sectors per thread)
+      const int y = it.ty * kTileRows + my, x = it.tx * kTileCols + mx;
       if (y < Ho && x < Wo) {
-        const size_t o = (((size_t)p * prm.Hs + y) * prm.Ws + x) * CO + ch0;
+        const size_t o = (((size_t)(pl * N + it.n) * prm.Hs + y) * prm.Ws + x) * CO;
         st_global_v8(prm.out_hi + o, h);
+        st_global_v8(prm.out_hi + o + 16, h + 8);
         st_global_v8(prm.out_lo + o, l);
+        st_global_v8(prm.out_lo + o + 16, l + 8);
       }
-    };
-    if (cur.it.n < N) { issue_loads(cur, am, ac); release_slot(cur); }
-    while (cur.it.n < N) {
-      Seq nx = cur; nx.advance(tiles_x, tiles_y);
-      if (nx.it.n < N) issue_loads(nx, bm, bc);
-      finish_tile(cur, am, ac);
-      cur = nx;
-      if (cur.it.n >= N) break;
-      release_slot(cur);
-      nx.advance(tiles_x, tiles_y);
-      if (nx.it.n < N) issue_loads(nx, am, ac);
-      finish_tile(cur, bm, bc);
-      cur = nx;
-      if (cur.it.n < N) release_slot(cur);
+     }
     }
   }
 
