@@ -35,9 +35,9 @@ constexpr int kEpiWarp0 = kBuilderWarps;              // warps 0-7 builders (the
 constexpr int kThreads = (kBuilderWarps + kEpiWarps) * 32;       // 512: four warps per scheduler, 128 registers per thread
 constexpr int CO = 32;                                // output channels
 constexpr int PH = 2 * kTileRows + 3, PW = 2 * kTileCols + 3;    // 35 x 19 input pixels
-constexpr int PPITCH = 24;                            // fp16 per row of a converted plane (19 used + zero slots 19-23; 12 words =
-                                                      // 48 bytes: the 64-bit loads of a half-warp (4 tile rows x 4 column pairs)
-                                                      // fall into 32 distinct banks)
+constexpr int PPITCH = 20;                            // fp16 per row of a converted plane (19 used + the zero slot 19; 10 words: the
+                                                      // im2col loads of a warp -- 4 row pairs, 4 plane rows apart -- fall into
+                                                      // 32 distinct banks)
 constexpr int PPLANE = PH * PPITCH;                   // fp16 per (colour plane, half)
 constexpr int RAW_PITCH = 64;                         // bytes per staged raw row: 19 pixels * 3 bytes + up to 3 bytes of misalignment
 constexpr int A_TILE = kTileM * 64;                   // 8 KB: 128 rows x 32 fp16
@@ -45,7 +45,7 @@ constexpr int STAGE_BYTES = 2 * A_TILE;               // hi + lo
 constexpr int GROUPS = 4;                             // builder groups (2 warps each) working on different items
 constexpr int GTHREADS = kBuilderWarps * 32 / GROUPS;  // 64
 constexpr int STAGES = 2 * GROUPS;                    // two A stages per group, alternating over the group's (item, plane) sequence
-constexpr int PATCH_BYTES = 3 * 2 * PPLANE * 2;       // 3 colour planes x (hi, lo) x fp16 = 10 080 B
+constexpr int PATCH_BYTES = 3 * 2 * PPLANE * 2;       // 3 colour planes x (hi, lo) x fp16 = 8 400 B
 constexpr int RAW_BYTES = PH * RAW_PITCH;             // 2 240 B
 constexpr int GROUP_BYTES = (PATCH_BYTES + RAW_BYTES + 15) / 16 * 16;
 constexpr int W_TILE = CO * 64;                       // 2 KB: 32 rows x 32 fp16
@@ -90,6 +90,15 @@ struct ItemIter {
     n += sn;
   }
 };
+
+// A word that straddles an end of the caller's buffer, assembled from its in-range bytes (at most two words per batch).
+__device__ __noinline__ uint32_t load_edge_word(const uint8_t* abase, int a, int lo, int hi) {
+  uint32_t v = 0u;
+#pragma unroll 1
+  for (int bb = 0; bb < 4; ++bb)
+    if (a + bb >= lo && a + bb < hi) v |= (uint32_t)__ldg(abase + a + bb) << (8 * bb);
+  return v;
+}
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GTHREADS) : "memory"); }
 
@@ -161,32 +170,33 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
     // aligned words that cover its 57 bytes.  Loads are unconditional from an always-valid (clamped) address, so all of
     // them are in flight together; rows / columns outside the image are zeroed at conversion (= TF SAME padding).  The
     // words of item k+1 are requested before item k is built, so their latency hides behind the im2col work.
-    const uintptr_t rgb0 = reinterpret_cast<uintptr_t>(prm.rgb), rgb_end = rgb0 + (size_t)N * H * W * 3;
-    const uintptr_t buf_lo = rgb0 & ~(uintptr_t)3;
-    const uintptr_t buf_hi = ((rgb_end + 3) & ~(uintptr_t)3) - 4;          // last aligned word that holds image bytes
+    // Byte offsets are 32-bit and relative to `abase`, the aligned word at or below the start of the batch (the launcher
+    // refuses batches of 2 GiB or more; the host side never forms them).
+    const int mis0 = (int)(reinterpret_cast<uintptr_t>(prm.rgb) & 3);
+    const uint8_t* abase = prm.rgb - mis0;
+    const int total = N * H * W * 3;
+    const int last_w = ((mis0 + total + 3) & ~3) - 4;                      // last aligned word that holds image bytes
     // the first / last word may straddle the ends of the caller's buffer (a batch that does not start or end on a 4-byte
     // boundary): those two words are assembled from in-range byte loads, every other word is one aligned 32-bit load
-    const uintptr_t full_lo = (rgb0 + 3) & ~(uintptr_t)3, full_hi = (rgb_end & ~(uintptr_t)3) - 4;
+    const int full_lo = mis0 ? 4 : 0, full_hi = ((mis0 + total) & ~3) - 4;
+    const int my_r = gt >> 4, my_wd4 = (gt & 15) * 4;                      // word i = gt + 64 q of the staged patch: row my_r + 4 q
     uint32_t rawreg[RAW_PER];
     auto load_raw = [&](const ItemIter& t) {
       const int iy0 = t.ty * kTileRows * 2 - prm.pad_t, ix0 = t.tx * kTileCols * 2 - prm.pad_l;
+      const int nH = t.n * H;
 #pragma unroll
       for (int q = 0; q < RAW_PER; ++q) {
-        const int i = gt + q * GTHREADS;                   // word i of the staged patch: row i / 16, word i % 16
-        const int r = i >> 4, wd = i & 15;
+        const int r = my_r + 4 * q;
         int iy = iy0 + r;
-        iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);         // rows outside the image: any valid row (masked at conversion)
-        const uintptr_t row0 = rgb0 + (((ptrdiff_t)t.n * H + iy) * W + ix0) * 3;
-        uintptr_t a = (row0 & ~(uintptr_t)3) + 4 * wd;
-        a = a < buf_lo ? buf_lo : (a > buf_hi ? buf_hi : a);
+        iy = min(max(iy, 0), H - 1);                       // rows outside the image: any valid row (masked at conversion)
+        const int row0 = mis0 + ((nH + iy) * W + ix0) * 3; // may be negative (left padding of the first row)
+        const int a = min(max((row0 & ~3) + my_wd4, 0), last_w);
         uint32_t v = 0u;
-        if (q < RAW_PER - 1 || i < RAW_WORDS) {
+        if (q < RAW_PER - 1 || r < PH) {
           if (a >= full_lo && a <= full_hi) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(a));
+            v = __ldg(reinterpret_cast<const uint32_t*>(abase + a));
           } else {
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb)
-              if (a + bb >= rgb0 && a + bb < rgb_end) v |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(a + bb)) << (8 * bb);
+            v = load_edge_word(abase, a, mis0, mis0 + total);
           }
         }
         rawreg[q] = v;
@@ -210,7 +220,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       // ---- conversion: every pixel normalised once, projected onto Y, Cb, Cr, split once per plane; two neighbouring pixels
       //      per step, so that their fp16 halves are stored as one 32-bit word per plane ----
       // byte address of patch pixel (0, 0); it may lie outside the buffer (padding), only its low two bits are used
-      const uint32_t img0_lo = (uint32_t)(rgb0 + (((ptrdiff_t)n * H + iy0) * W + ix0) * 3);
+      const uint32_t img0_lo = (uint32_t)(mis0 + ((n * H + iy0) * W + ix0) * 3);
       const uint32_t row_bytes = (uint32_t)W * 3u;
       uint32_t* planes_w = reinterpret_cast<uint32_t*>(planes_s);
 #pragma unroll
@@ -227,10 +237,15 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
             // the staged row starts at the aligned word below byte (iy, ix0); this pixel sits (row0 & 3) + 3 pc bytes in
             // (a clamped row or word holds other bytes, but only for pixels that are masked out below)
             const uint32_t mis = (img0_lo + (uint32_t)(iy - iy0) * row_bytes) & 3u;
-            const uint8_t* px = raw_s + pr * RAW_PITCH + mis + 3 * pc;
+            // the six bytes of the pixel pair: three aligned words, funnel-shifted by the byte misalignment
+            const uint32_t boff = (uint32_t)(pr * RAW_PITCH + 3 * pc) + mis;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw_s + (boff & ~3u));
+            const uint32_t sh = (boff & 3u) * 8u;
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            const uint32_t p03 = __funnelshift_r(w0, w1, sh), p45 = __funnelshift_r(w1, w2, sh);
             // x.astype(float32)/255, then (t0*k0 + t1*k1) + t2*k2 with separate roundings, then + offset
-            const float r0 = div255(px[0]), g0 = div255(px[1]), b0 = div255(px[2]);
-            const float r1 = div255(px[3]), g1 = div255(px[4]), b1 = div255(px[5]);
+            const float r0 = div255(p03 & 0xffu), g0 = div255((p03 >> 8) & 0xffu), b0 = div255((p03 >> 16) & 0xffu);
+            const float r1 = div255(p03 >> 24), g1 = div255(p45 & 0xffu), b1 = div255((p45 >> 8) & 0xffu);
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) {
               v0[pl] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0, prm.cc.k[pl][0]), __fmul_rn(g0, prm.cc.k[pl][1])),
@@ -270,32 +285,36 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
         const uint32_t* ph_w = reinterpret_cast<const uint32_t*>(planes_s + (pl * 2 + 0) * PPLANE);
         const uint32_t* pl_w = reinterpret_cast<const uint32_t*>(planes_s + (pl * 2 + 1) * PPLANE);
         {
-          // a thread builds the rows of two horizontally neighbouring output pixels (r, c) and (r, c + 1), c even: their
-          // kernel-row windows (input columns 2c .. 2c+5 and 2c+2 .. 2c+7) lie in 16 aligned bytes of the plane row, i.e. two
-          // 64-bit loads per (kernel row, half) serve both rows -- words 0-2 for the first, words 1-3 for the second.
-          // K slot 6 kh + s = input pixel (2r + kh, 2c + s)
-          const int r = gt >> 2, c = (gt & 3) * 2;
-          const int m = r * kTileCols + c;
-          const int w0 = (2 * r) * (PPITCH / 2) + c;                 // word index of input pixel (2r, 2c)
-          uint32_t hw[2][16], lw[2][16];
+          // a thread builds the rows of two vertically neighbouring output pixels (r, c) and (r + 1, c), r even: their 5 x 6
+          // input windows (input rows 2r .. 2r+4 and 2r+2 .. 2r+6, columns 2c .. 2c+5) share three of seven rows, so 21 aligned
+          // 32-bit loads per half serve both.  K slot 6 kh + s = input pixel (2r + kh, 2c + s).  Eight consecutive threads
+          // hold one tile row (c = 0..7): their 16-byte stores fall on the eight distinct chunks of a 128-byte swizzle atom
+          // pair, and a warp's loads (4 row pairs x 8 columns, 40 words apart) on 32 distinct banks.
+          const int rp = gt >> 3, c = gt & 7;
+          const int m = rp * 2 * kTileCols + c;
+          const int w0 = (4 * rp) * (PPITCH / 2) + c;                // word index of input pixel (4 rp, 2c)
+          uint32_t hw[7][3], lw[7][3];
 #pragma unroll
-          for (int kh = 0; kh < 5; ++kh) {
-            const uint2 h01 = *reinterpret_cast<const uint2*>(ph_w + w0 + kh * (PPITCH / 2));
-            const uint2 h23 = *reinterpret_cast<const uint2*>(ph_w + w0 + kh * (PPITCH / 2) + 2);
-            const uint2 l01 = *reinterpret_cast<const uint2*>(pl_w + w0 + kh * (PPITCH / 2));
-            const uint2 l23 = *reinterpret_cast<const uint2*>(pl_w + w0 + kh * (PPITCH / 2) + 2);
-            hw[0][3 * kh] = h01.x; hw[0][3 * kh + 1] = h01.y; hw[0][3 * kh + 2] = h23.x;
-            hw[1][3 * kh] = h01.y; hw[1][3 * kh + 1] = h23.x; hw[1][3 * kh + 2] = h23.y;
-            lw[0][3 * kh] = l01.x; lw[0][3 * kh + 1] = l01.y; lw[0][3 * kh + 2] = l23.x;
-            lw[1][3 * kh] = l01.y; lw[1][3 * kh + 1] = l23.x; lw[1][3 * kh + 2] = l23.y;
-          }
+          for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              hw[k][s] = ph_w[w0 + k * (PPITCH / 2) + s];
+              lw[k][s] = pl_w[w0 + k * (PPITCH / 2) + s];
+            }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            hw[e][15] = 0u; lw[e][15] = 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(a_hi + sw64(m + e, j)) = make_uint4(hw[e][4 * j], hw[e][4 * j + 1], hw[e][4 * j + 2], hw[e][4 * j + 3]);
-              *reinterpret_cast<uint4*>(a_lo + sw64(m + e, j)) = make_uint4(lw[e][4 * j], lw[e][4 * j + 1], lw[e][4 * j + 2], lw[e][4 * j + 3]);
+              // words 4j .. 4j+3 of the row: word q = (kernel row q / 3, pixel pair q % 3); word 15 = K slots 30, 31 = zero
+              uint32_t vh[4], vl[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int wq = 4 * j + q;
+                vh[q] = wq < 15 ? hw[2 * e + wq / 3][wq % 3] : 0u;
+                vl[q] = wq < 15 ? lw[2 * e + wq / 3][wq % 3] : 0u;
+              }
+              *reinterpret_cast<uint4*>(a_hi + sw64(m + e * kTileCols, j)) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+              *reinterpret_cast<uint4*>(a_lo + sw64(m + e * kTileCols, j)) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
             }
           }
         }
@@ -405,6 +424,7 @@ cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_fl
   const int tiles_x = (prm.Wo + kTileCols - 1) / kTileCols, tiles_y = (prm.Ho + kTileRows - 1) / kTileRows;
   const long long items = (long long)tiles_x * tiles_y * prm.N;      // one item = one tile of one image, all three planes
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (prm.rgb && (long long)prm.N * prm.H * prm.W * 3 > 0x7ffffff0LL) return cudaErrorInvalidValue;   // 32-bit byte offsets in the builders
   const int grid = items < num_sms ? (int)items : num_sms;
   if (prm.rgb) k_tc_conv1<0><<<grid, kThreads, SMEM_BYTES, stream>>>(prm, tiles_x, tiles_y, (int)items, error_flag);
   else k_tc_conv1<1><<<grid, kThreads, SMEM_BYTES, stream>>>(prm, tiles_x, tiles_y, (int)items, error_flag);
