@@ -49,6 +49,12 @@ FLOP_PER_PX = {"conv1": 1200, "conv2": 19200, "conv3": 13824, "conv4": 13824, "c
                "dconv5": 13824, "dconv6": 13824, "dconv7": 38400, "dconv8": 2400}
 BYTES_PER_PX = {"conv1": 3 + 96, "dconv8": 192 + 3, "hist": 1.5, "latent_expand": 1.5 + 6, "quantise": 7.5}
 HBM_BOUND = ("conv1", "dconv8", "hist", "latent_expand", "quantise")
+# The decoder's default path runs dconv8's tap-response GEMM inside dconv7 (which then writes 25 fp32 responses per output
+# pixel instead of 64 split activations) and "dconv8" is the gather + colour + pack pass over those responses:
+# 3 planes x 25 x 4 B / 4 final pixels = 75 B read + 3 B written per RGB pixel.  NNIC_FUSE_D78=0 restores the two-kernel form.
+if os.environ.get("NNIC_FUSE_D78", "1") != "0":
+    FLOP_PER_PX["dconv7"] += FLOP_PER_PX.pop("dconv8")
+    BYTES_PER_PX["dconv8"] = 75 + 3
 
 
 def measured_peaks(burst):

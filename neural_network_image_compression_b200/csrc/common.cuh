@@ -35,6 +35,11 @@ __device__ __forceinline__ void split2_f32(float v0, float v1, uint32_t& hi2, ui
 __device__ __forceinline__ float join_f32(__half hi, __half lo) {
   return (__half2float(hi) + __half2float(lo)) * ACT_INV_SCALE;
 }
+// programmatic dependent launch (kernels.h launch_kernel): let the next kernel of the stream start its prologue; wait until every
+// earlier kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // leaky_relu as TF computes it in fp32: one rounded multiply on the negative side.
 __device__ __forceinline__ float leaky(float v) { return v > 0.0f ? v : __fmul_rn(v, LEAKY_ALPHA); }
 

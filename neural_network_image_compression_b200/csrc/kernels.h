@@ -23,6 +23,23 @@ inline bool first_use_on_device(unsigned long long& seen_mask) {
 }
 
 
+// Programmatic dependent launch (NNIC_PDL=0 switches it off): a kernel launched through launch_kernel(..., pdl = true) may start
+// while the previous kernel of the stream is still running -- its prologue (barrier init, TMEM allocation, weight and bias
+// staging) overlaps the predecessor's tail -- and must execute pdl_wait() (common.cuh) before it touches anything an earlier
+// kernel writes or reads.  Every such kernel also executes pdl_trigger() at its start.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 struct ColourConsts {
   float k[3][3];     // RGB -> YCbCr rows   (float)(ycbcr_kernel)      utils.py:7
   float kinv[3][3];  // YCbCr -> RGB rows   (float)(inv(ycbcr_kernel)) utils.py:8
@@ -146,6 +163,13 @@ struct TcPatchParams {
   __half* out_hi;
   __half* out_lo;
   float* out_f32;
+  // dconv7 fused with dconv8's response GEMM (decoder.py:16-17): instead of the activation, the layer writes
+  // f8_out = R [P][tile][25 taps][4 output phases][128 tile pixels] fp32, R = x . K8[tap] per dconv7 output pixel, tiles of 16 x 8
+  // pixels of the Hp x Wp input grid in row-major order (read by launch_dconv8_gather);
+  // f8_w_hi / f8_w_lo: dconv8's [2 sets][32 taps (25 used)][64] fp16 matrices
+  float* f8_out;
+  const __half* f8_w_hi;
+  const __half* f8_w_lo;
 };
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes);
 // a_hi / a_lo: plain activation views with box [Cin, 10, 1, 18, 1]; row_bytes = 2*Cin (128 or 64)
@@ -188,5 +212,9 @@ struct TcDconv8Params {
 cudaError_t launch_tc_dconv8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                              const CUtensorMap& w_lo, const TcDconv8Params& prm, int num_sms, int* error_flag,
                              cudaStream_t stream);
+
+// dconv8 behind the fused dconv7 (TcPatchParams::f8_out): R [3N][tile][25][4][128] fp32 -> rgb / prequant / planes_out as above,
+// prm.Hi / prm.Wi = 2Hp x 2Wp.
+cudaError_t launch_dconv8_gather(const float* R, const TcDconv8Params& prm, int Hp, int Wp, cudaStream_t stream);
 
 }  // namespace nnic

@@ -37,6 +37,9 @@ inline const LayerSpec& spec_of(int set, int layer) { return set < 2 ? kEnc[laye
 inline const LayerSpec& gemm_spec(int net, int gi) { return net == 0 ? kEnc[gi + 1] : (net == 1 ? kDec[gi] : kEnt[gi]); }
 
 thread_local std::string g_global_error = "";
+}  // namespace
+namespace nnic { int g_pdl = 1; }     // programmatic dependent launch between consecutive kernels (kernels.h launch_kernel; NNIC_PDL=0: off)
+namespace {
 
 // kernel ids reported by nnic_profile_collect (keep in sync with include/nnic.h NNIC_KERNEL_*)
 enum { K_CONV1 = 0, K_CONV2, K_CONV3, K_CONV4, K_CONV8, K_QUANTISE, K_EXPAND, K_DCONV1, K_DCONV5, K_DCONV6, K_DCONV7,
@@ -85,6 +88,8 @@ struct nnic_handle {
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   bool int_latent = true;           // dconv1 multiplies the integer symbols and folds /255 into its epilogue (NNIC_INT_LATENT=0: x/255 split in two planes)
   bool a_hi_only = false;           // set around dconv1's launch by decode_batch when its input is the integer symbol plane
+  bool fuse_d78 = true;             // dconv7 feeds dconv8's response GEMM on chip (NNIC_FUSE_D78=0: dconv7's output goes through memory)
+  float* fuse8_out = nullptr;       // set around dconv7's launch by decode_batch: the response tensor R it writes instead of its output
   EncodeTiledFn encode_tiled = nullptr;
   unsigned long long wait_timeout = 4000000000ull;   // barrier-wait bound in SM cycles (NNIC_TC_TIMEOUT_MS, 0 = none)
   int hist_variant = 0;             // NNIC_HIST_VARIANT (development): copies * 100 + blocks per SM of k_hist
@@ -653,6 +658,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.wait_timeout = h->wait_timeout;
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
+    if (h->fuse8_out) { pp.f8_out = h->fuse8_out; pp.f8_w_hi = h->d8_w_hi; pp.f8_w_lo = h->d8_w_lo; }
     const bool prof = h->tc_prof;
     const size_t prof_words = (size_t)h->num_sms * 4 * 8;
     if (prof) {
@@ -670,9 +676,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       const int nb_ = h->num_sms;
       for (int b = 0; b < nb_; ++b) for (int r = 0; r < 4; ++r) for (int k = 0; k < 8; ++k) a[r][k] += hb[((size_t)b * 4 + r) * 8 + k] / (double)nb_;
       fprintf(stderr, "[tcprof %s] producer: total %.0f wait_patch_empty %.0f wait_w_empty %.0f | mmaA: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | "
-              "mmaB: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | epi: total %.0f wait_full %.0f tmem+add %.0f out %.0f\n",
+              "mmaB: total %.0f wait_patch %.0f wait_slot %.0f wait_w %.0f issue %.0f | epi: total %.0f wait_full %.0f tmem+add %.0f out %.0f (fused dconv8: wait_a %.0f write_a %.0f drain %.0f)\n",
               sp.name, a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[1][3], a[1][4], a[2][0], a[2][1], a[2][2], a[2][3], a[2][4],
-              a[3][0], a[3][1], a[3][2], a[3][3]);
+              a[3][0], a[3][1], a[3][2], a[3][3], a[3][4], a[3][5], a[3][6]);
     }
     return 0;
   }
@@ -764,20 +770,35 @@ int encode_batch(nnic_t* h, const uint8_t* rgb, const float* planes, int nb, int
   return 0;
 }
 
+// dconv7's fused output: 16 x 8-pixel tiles of its INPUT grid (2lh x 2lw), 25 taps x 4 phases x 128 pixels fp32 per tile
+size_t d78_response_bytes(size_t P, int lh, int lw) {
+  const size_t tiles = (size_t)((2 * lh + 15) / 16) * ((2 * lw + 7) / 8);
+  return pad1k(P * tiles * 12800 * 4);
+}
+size_t dec_act_need(bool split, size_t P, int lh, int lw) {
+  const size_t d4 = act_bytes(split, P, 4 * lh, 4 * lw, 64), resp = d78_response_bytes(P, lh, lw);
+  return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + (d4 > resp ? d4 : resp) + 16384;
+}
+
 // ---- decoder for one micro-batch -----------------------------------------------------------------
 int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, int lh, int lw, uint8_t* rgb,
                  float* prequant, float* out_planes, cudaStream_t st) {
   const bool split = h->arith == NNIC_ARITH_TC_SPLIT;
   const int P = 3 * nb;
-  const size_t need = act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) +
-                      act_bytes(split, P, 4 * lh, 4 * lw, 64) + 8192;
+  const size_t need = dec_act_need(split, P, lh, lw) - 8192;
   size_t base_used = h->arena_used;
   if (h->arena.bytes < base_used + need) return fail(h, NNIC_ERR_CUDA, "internal: arena too small (%zu < %zu)", h->arena.bytes, base_used + need);
   Act d0 = take_act(h, split, P, lh, lw, 32);
   Act d1 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
   Act d2 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
   Act d3 = take_act(h, split, P, 2 * lh, 2 * lw, 64);
-  Act d4 = take_act(h, split, P, 4 * lh, 4 * lw, 64);
+  // dconv7 + dconv8: dconv7 hands its tiles to dconv8's response GEMM on chip and writes R, 25 fp32 tap responses per output
+  // pixel (100 bytes instead of 256) in tile-blocked order [P][tile][25][4 phases][128 pixels], which k_dconv8_gather turns into RGB
+  const bool fuse78 = split && h->tc_dconv8 && h->fuse_d78 && !h->decode_fp16 && h->tc_cluster != 2;
+  Act d4; d4.H = 4 * lh; d4.W = 4 * lw; d4.C = 64; d4.Hs = d4.H; d4.Ws = d4.W;
+  float* resp = nullptr;
+  if (fuse78) resp = (float*)arena_take(h, d78_response_bytes(P, lh, lw));
+  else d4 = take_act(h, split, P, 4 * lh, 4 * lw, 64);
   // u8 latent into the tensor-core decoder: the symbols go in as exact fp16 integers (one plane, one product less per MAC)
   const bool int_latent = latent && split && !h->decode_fp16 && h->int_latent;
   if (latent) {
@@ -793,8 +814,20 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   if (rc_d1) return rc_d1;
   if (int rc = run_gemm_layer(h, 1, 1, d1, d2, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
   if (int rc = run_gemm_layer(h, 1, 2, d2, d3, &d1, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
-  if (int rc = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st)) return rc;
-  if (split && h->tc_dconv8) {
+  h->fuse8_out = resp;
+  const int rc_d7 = run_gemm_layer(h, 1, 3, d3, d4, nullptr, P, nb, TC_OUT_SPLIT, nullptr, nullptr, nullptr, st);
+  h->fuse8_out = nullptr;
+  if (rc_d7) return rc_d7;
+  if (fuse78) {
+    TcDconv8Params dp;
+    memset(&dp, 0, sizeof dp);
+    dp.N = nb; dp.Hi = 4 * lh; dp.Wi = 4 * lw;
+    dp.inv_scale[0] = h->d8_inv_scale[0]; dp.inv_scale[1] = h->d8_inv_scale[1];
+    dp.bias[0] = h->b_edge[1][0]; dp.bias[1] = h->b_edge[1][1];
+    dp.cc = colour_consts();
+    dp.rgb = rgb; dp.prequant = prequant; dp.planes_out = out_planes;
+    CKL(h, K_DCONV8, st, launch_dconv8_gather(resp, dp, 2 * lh, 2 * lw, st));
+  } else if (split && h->tc_dconv8) {
     const CUtensorMap *ma_hi = nullptr, *ma_lo = nullptr;
     if (int rc = cached_act_maps(h, 15, &ma_hi, &ma_lo, d4.hi, d4.lo, P, 4 * lh, 4 * lw, 64, false, 64, 128, 8, 16, d4.Hs, d4.Ws)) return rc;
     TcDconv8Params dp;
@@ -810,7 +843,8 @@ int decode_batch(nnic_t* h, const uint8_t* latent, const float* planes, int nb, 
   } else {
     CKL(h, K_DCONV8, st, launch_dconv8(d4.hi, d4.lo, d4.f32, nb, 4 * lh, 4 * lw, h->w_edge[1].data(), h->b_edge[1].data(), rgb, prequant, out_planes, st));
   }
-  record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P); record_dbg(h, 8, d4, P);
+  record_dbg(h, 4, d0, P); record_dbg(h, 5, d1, P); record_dbg(h, 6, d2, P); record_dbg(h, 7, d3, P);
+  if (fuse78) h->dbg[8] = {}; else record_dbg(h, 8, d4, P);       // fused: dconv7's output exists on chip only
   h->arena_used = base_used;
   return 0;
 }
@@ -831,9 +865,7 @@ size_t enc_act_need(bool split, size_t P, int H, int W) {
   return act_bytes(split, P, even_up(H1), even_up(W1), 32) + 3 * act_bytes(split, P, even_up(H2), even_up(W2), 64) +
          act_bytes(false, P, H3, W3, 32) + 16384;
 }
-size_t dec_act_need(bool split, size_t P, int lh, int lw) {
-  return act_bytes(split, P, lh, lw, 32) + 3 * act_bytes(split, P, 2 * lh, 2 * lw, 64) + act_bytes(split, P, 4 * lh, 4 * lw, 64) + 16384;
-}
+
 
 // ---- Entropynet (tf2_0/src/training.py:25-42) -------------------------------------------------------------------
 int finalize_entropynet(nnic_t* h) {
@@ -908,6 +940,8 @@ int nnic_create(int device, nnic_t** out) {
   if (const char* env = getenv("NNIC_TC_DCONV8")) h->tc_dconv8 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_INT_LATENT")) h->int_latent = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_FUSE_D78")) h->fuse_d78 = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_PDL")) nnic::g_pdl = atoi(env) != 0;    // process-wide
   if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env);
   if (const char* env = getenv("NNIC_TC_DBG")) h->tc_dbg = atoi(env);
   if (const char* env = getenv("NNIC_HIST_VARIANT")) h->hist_variant = atoi(env);

@@ -448,6 +448,8 @@ template <int OUT_KIND>
 __global__ void __launch_bounds__(256) k_latent_expand(const uint8_t* __restrict__ latent, int N, size_t pix,
                                                        __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                        float* __restrict__ out_f32) {
+  pdl_trigger();
+  pdl_wait();
   // one thread = 16 channels of one (pixel, plane): one 128-bit load; 6 threads per latent pixel
   const size_t total = (size_t)N * pix * 6;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -494,10 +496,9 @@ cudaError_t launch_latent_expand(const uint8_t* latent, int N, int lh, int lw, _
                                  float* out_f32, bool integer_symbols, cudaStream_t stream) {
   const size_t pix = (size_t)lh * lw;
   const int grid = grid_for((size_t)N * pix * 6, 256);
-  if (out_hi && integer_symbols) k_latent_expand<2><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, nullptr, nullptr);
-  else if (out_hi) k_latent_expand<1><<<grid, 256, 0, stream>>>(latent, N, pix, out_hi, out_lo, nullptr);
-  else k_latent_expand<0><<<grid, 256, 0, stream>>>(latent, N, pix, nullptr, nullptr, out_f32);
-  return cudaGetLastError();
+  if (out_hi && integer_symbols) return launch_kernel(k_latent_expand<2>, dim3(grid), dim3(256), 0, stream, true, latent, N, pix, out_hi, (__half*)nullptr, (float*)nullptr);
+  if (out_hi) return launch_kernel(k_latent_expand<1>, dim3(grid), dim3(256), 0, stream, true, latent, N, pix, out_hi, out_lo, (float*)nullptr);
+  return launch_kernel(k_latent_expand<0>, dim3(grid), dim3(256), 0, stream, true, latent, N, pix, (__half*)nullptr, (__half*)nullptr, out_f32);
 }
 
 __global__ void __launch_bounds__(256) k_f32_to_split(const float* __restrict__ in, size_t count4,
@@ -738,6 +739,8 @@ cudaError_t launch_hist_channels(const uint8_t* latent, size_t total_pixels, uns
 // hist_global[i] += sum over images of hist[n][i]; blockIdx.y strides over the images, one 64-bit atomic per block and bin
 __global__ void __launch_bounds__(256) k_hist_reduce(const uint32_t* __restrict__ hist, int N,
                                                      unsigned long long* __restrict__ hist_global) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * 256 + threadIdx.x;   // 0..767
   unsigned long long s = 0;
   for (int n = blockIdx.y; n < N; n += gridDim.y) s += hist[(size_t)n * 768 + i];
@@ -745,8 +748,7 @@ __global__ void __launch_bounds__(256) k_hist_reduce(const uint32_t* __restrict_
 }
 cudaError_t launch_hist_reduce(const uint32_t* hist, int N, unsigned long long* hist_global, cudaStream_t stream) {
   const int slices = N < 148 ? N : 148;
-  k_hist_reduce<<<dim3(3, slices < 1 ? 1 : slices), 256, 0, stream>>>(hist, N, hist_global);
-  return cudaGetLastError();
+  return launch_kernel(k_hist_reduce, dim3(3, slices < 1 ? 1 : slices), dim3(256), 0, stream, true, hist, N, hist_global);
 }
 
 // One block of 256 threads per histogram row (one thread per bin).
@@ -785,6 +787,8 @@ __device__ __forceinline__ float entropy_row(const CountT* __restrict__ row, flo
 __global__ void __launch_bounds__(256) k_entropy_u32(const uint32_t* __restrict__ hist, float symbols_per_plane,
                                                      float pixels, float* __restrict__ entropy, float* __restrict__ bpp) {
   __shared__ float red[256];
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x;
   float e[3];
   for (int p = 0; p < 3; ++p) e[p] = entropy_row(hist + ((size_t)n * 3 + p) * 256, red);
@@ -805,8 +809,7 @@ __global__ void __launch_bounds__(256) k_entropy_u64(const unsigned long long* _
 }
 cudaError_t launch_entropy_u32(const uint32_t* hist, int N, float symbols_per_plane, float pixels, float* entropy,
                                float* bpp, cudaStream_t stream) {
-  k_entropy_u32<<<N, 256, 0, stream>>>(hist, symbols_per_plane, pixels, entropy, bpp);
-  return cudaGetLastError();
+  return launch_kernel(k_entropy_u32, dim3(N), dim3(256), 0, stream, true, hist, symbols_per_plane, pixels, entropy, bpp);
 }
 cudaError_t launch_entropy_u64(const unsigned long long* counts, int rows, float* entropy, cudaStream_t stream) {
   k_entropy_u64<<<rows, 256, 0, stream>>>(counts, entropy);

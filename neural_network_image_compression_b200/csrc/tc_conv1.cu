@@ -123,6 +123,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = prm.N, H = prm.H, W = prm.W, Ho = prm.Ho, Wo = prm.Wo;
   (void)num_items;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
@@ -146,6 +147,7 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                  // everything above only touched shared memory, TMEM and the (static) weights
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kBuilderWarps) {
@@ -426,9 +428,8 @@ cudaError_t launch_tc_conv1(const TcConv1Params& prm, int num_sms, int* error_fl
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   if (prm.rgb && (long long)prm.N * prm.H * prm.W * 3 > 0x7ffffff0LL) return cudaErrorInvalidValue;   // 32-bit byte offsets in the builders
   const int grid = items < num_sms ? (int)items : num_sms;
-  if (prm.rgb) k_tc_conv1<0><<<grid, kThreads, SMEM_BYTES, stream>>>(prm, tiles_x, tiles_y, (int)items, error_flag);
-  else k_tc_conv1<1><<<grid, kThreads, SMEM_BYTES, stream>>>(prm, tiles_x, tiles_y, (int)items, error_flag);
-  return cudaGetLastError();
+  return launch_kernel(prm.rgb ? k_tc_conv1<0> : k_tc_conv1<1>, dim3(grid), dim3(kThreads), SMEM_BYTES, stream, true, prm, tiles_x, tiles_y,
+                       (int)items, error_flag);
 }
 
 }  // namespace nnic

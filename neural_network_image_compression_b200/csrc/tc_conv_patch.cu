@@ -37,24 +37,34 @@ constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
 constexpr int GTAPS = 3;                                     // taps per accumulation chain
-constexpr int WSLOTS = 8;                                    // weight tiles (one tap each) in flight
 constexpr int TMEM_COLS = 512;
+constexpr int F8_NT = 32;                                    // FUSE8: dconv8's 25 taps padded to the MMA N granularity
 
 // RB = bytes of one pixel row of the patch (64 input channels -> 128, SWIZZLE_128B; 32 -> 64, SWIZZLE_64B)
-template <int RB, int NSPLIT, int COUT>
+// FUSE8 (dconv7 only): the epilogue hands its output tile to a second GEMM -- dconv8's tap responses, see the kernel -- which
+// takes three weight-ring slots worth of shared memory (A tile hi + lo 32 KB, both dconv8 weight sets 16 KB) and one
+// accumulation slot's worth of TMEM columns.
+template <int RB, int NSPLIT, int COUT, bool FUSE8 = false>
 struct PCfg {
+  static constexpr int WSLOTS = FUSE8 ? 5 : 8;                           // weight tiles (one tap each) in flight
   static constexpr int SLOT_COLS = 2 * COUT;                             // one accumulation chain: [main | correction]
-  static constexpr int SLOTS = 512 / SLOT_COLS > 8 ? 8 : 512 / SLOT_COLS;
+  static constexpr int SLOTS = FUSE8 ? 3 : (512 / SLOT_COLS > 8 ? 8 : 512 / SLOT_COLS);
+  static constexpr int F8_COL = SLOTS * SLOT_COLS;                       // FUSE8: TMEM columns [main 32 | correction 32] of the tap responses
   static constexpr int kEpiWarps = 4 * NSPLIT;                          // NSPLIT warps per TMEM lane group, COUT/NSPLIT channels each
   static constexpr int kPatchWarp = kEpiWarp0 + kEpiWarps;
-  static constexpr int kThreads = (kPatchWarp + 1) * 32;
+  static constexpr int kF8Warp = kPatchWarp + 1;                         // FUSE8: issuer of the response MMAs
+  static constexpr int kThreads = (kPatchWarp + 1 + (FUSE8 ? 1 : 0)) * 32;
   static constexpr int KSTEPS = RB / 32;                                 // 16-element k-steps per tap
   static constexpr int PATCH_TX = PH * PW * RB;                          // bytes one patch load brings
   static constexpr int PATCH_SLOT = (PATCH_TX + 1023) / 1024 * 1024;
   static constexpr int SET_BYTES = 2 * PATCH_SLOT;                       // hi + lo
   static constexpr int W_TILE = COUT * RB;                               // one of hi / lo
   static constexpr int W_SLOT = 2 * W_TILE;                              // one tap: [W_hi | W_lo]
-  static constexpr int BAR_OFF = NSETS * SET_BYTES + WSLOTS * W_SLOT;
+  static constexpr int F8_A_OFF = NSETS * SET_BYTES + WSLOTS * W_SLOT;   // FUSE8: [A_hi | A_lo], 128 pixels x 64 channels fp16 each
+  static constexpr int F8_A_TILE = kTileM * 128;
+  static constexpr int F8_W_OFF = F8_A_OFF + 2 * F8_A_TILE;              // FUSE8: [set][W_hi | W_lo], 32 taps x 64 channels fp16 each
+  static constexpr int F8_W_SET = 2 * F8_NT * 128;
+  static constexpr int BAR_OFF = FUSE8 ? F8_W_OFF + 2 * F8_W_SET : F8_A_OFF;
   static constexpr int HIST_OFF = BAR_OFF + 512 + 2 * COUT * 4;          // conv8: 256-bin histogram of the tile being quantised
   static constexpr int SMEM_BYTES = HIST_OFF + 1024 + 1024;
   static constexpr uint32_t A_SBO = PW * RB;                             // 8-row group stride of a tap view: one patch row
@@ -88,12 +98,21 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
 // AHI: the input activations are EXACT in one fp16 plane (dconv1 fed with the integer latent symbols 0..255, see
 // nnic_api.cu decode_batch): no lo patch is loaded and the A_lo x W_hi product is not issued; everything else as in the
 // split arithmetic (A_hi x [W_hi | W_lo], main + correction halves, split output).
-template <int RB, int NSPLIT, int COUT, bool FAST, int CL, bool AHI>
-__global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT>::kThreads), 1)
+// FUSE8 (dconv7, decoder.py:16-17,30-32): the layer's output never goes to memory.  dconv8 has ONE output channel, so it is a
+// GEMM over its INPUT pixels, R[pixel, tap] = sum_ci x[pixel, ci] K8[tap, ci] (tc_dconv8.cu), and every (pixel, tap) response
+// feeds exactly one output pixel.  The epilogue therefore writes each finished phase tile (128 pixels x 64 channels, hi and lo)
+// into shared memory as an A operand, one thread issues the same eight MMAs k_tc_dconv8 would (A_hi x [K8_hi | K8_lo],
+// A_lo x K8_hi per k-step, so the responses are bit-identical to the unfused path), and one phase later the epilogue warps move
+// the 25 responses per pixel from TMEM to global memory (tile-blocked, so a warp writes whole 128-byte lines): 100 bytes per
+// pixel instead of 256, read once by k_dconv8_gather.
+template <int RB, int NSPLIT, int COUT, bool FAST, int CL, bool AHI, bool FUSE8>
+__global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT, FUSE8>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
-  using C = PCfg<RB, NSPLIT, COUT>;
+  using C = PCfg<RB, NSPLIT, COUT, FUSE8>;
+  static_assert(!FUSE8 || (RB == 128 && NSPLIT == 4 && COUT == 64 && !FAST && CL == 1 && !AHI), "FUSE8 is dconv7's variant");
+  constexpr int WSLOTS = C::WSLOTS;
   const WaitCtx wc{error_flag, prm.wait_timeout};
   constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
@@ -110,24 +129,39 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* w_empty = w_full + WSLOTS;         // [WSLOTS]
   uint64_t* slot_full = w_empty + WSLOTS;      // [SLOTS]
   uint64_t* slot_empty = slot_full + SLOTS;    // [SLOTS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_empty + SLOTS);
+  uint64_t* f8_a_empty = slot_empty + SLOTS;   // FUSE8: the response MMAs have read the A tile
+  uint64_t* f8_r_full = f8_a_empty + 1;        // FUSE8: the responses of a phase tile are in TMEM
+  uint64_t* f8_a_full = f8_r_full + 1;         // FUSE8: every epilogue warp has written its rows of the A tile (and drained the previous responses)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f8_a_full + 1);
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 512);
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem + C::HIST_OFF);
-  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS) * 8 + 4 <= 512, "barrier area too small");
+  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS + 3) * 8 + 4 <= 512, "barrier area too small");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSETS; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kNumMma); }
     for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], kEpiWarps); }
+    mbar_init(f8_a_empty, 1); mbar_init(f8_r_full, 1); mbar_init(f8_a_full, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
   }
   for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) bias_s[i] = prm.bias[i];
   for (int i = threadIdx.x; i < 256; i += kThreads) hist_s[i] = 0;
+  if (FUSE8) {
+    // both dconv8 weight sets stay resident: [set][K8_hi rows 0-31 | K8_lo rows 32-63], 128-byte rows in the SWIZZLE_128B
+    // pattern (16-byte chunk c of row r at chunk c ^ (r & 7)), as TMA would have written them
+    for (int i = threadIdx.x; i < 2 * 64 * 8; i += kThreads) {
+      const int set = i >> 9, r = (i >> 3) & 63, c = i & 7;
+      const __half* src = (r < 32 ? prm.f8_w_hi : prm.f8_w_lo) + ((size_t)(set * F8_NT + (r & 31)) * 64 + c * 8);
+      *reinterpret_cast<uint4*>(smem + C::F8_W_OFF + set * C::F8_W_SET + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(src);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -136,6 +170,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   if (CL > 1) cluster_sync();                  // the peer's barriers exist before anything is multicast to them
+  pdl_wait();                                  // everything above only touched shared memory, TMEM and the (static) weights
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_plane = tiles_x * tiles_y;
   // cluster rounds: the CTAs of a cluster take items base + rank; a CTA without an item in the last round still mirrors
@@ -295,6 +330,32 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
     }
     if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
+  } else if (FUSE8 && warp == C::kF8Warp) {
+    // ===================== FUSE8: issuer of dconv8's response MMAs =====================
+    const uint64_t a_hi = make_smem_desc<128>(smem_u32(smem + C::F8_A_OFF));
+    const uint64_t a_lo = a_hi + (uint64_t)(C::F8_A_TILE >> 4);
+    const uint32_t d_tmem = tmem_base + C::F8_COL;
+    uint32_t k = 0;
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int set = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
+      const uint64_t w_hl = make_smem_desc<128>(smem_u32(smem + C::F8_W_OFF + set * C::F8_W_SET));
+      for (int j = 0; j < prm.njobs; ++j, ++k) {
+        if (DBG(2048)) continue;
+        mbar_wait(f8_a_full, k & 1, wc, 9);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (DBG(4096)) break;
+            umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, make_idesc(2 * F8_NT), ks ? 1u : 0u);   // A_hi x [K8_hi | K8_lo]
+            umma_f16(d_tmem + F8_NT, a_lo + 2 * ks, w_hl + 2 * ks, make_idesc(F8_NT), 1u);          // A_lo x K8_hi
+          }
+          umma_commit(f8_a_empty);
+          umma_commit(f8_r_full);
+        }
+        __syncwarp();
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     constexpr int HALF = COUT / NSPLIT;       // channels per thread
@@ -303,6 +364,30 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int ch0 = hf * HALF;
     int slot = 0; uint32_t slot_phase = 0;
     long long tw_full = 0, t_ld = 0, t_out = 0, t_begin = TICK();
+    long long t_f8_wait = 0, t_f8_st = 0, t_f8_drain = 0;
+    // FUSE8: number of phase tiles handed to the response GEMM so far, and where the responses of the latest one belong
+    uint32_t f8_count = 0;
+    size_t f8_prev_off = 0; bool f8_prev_valid = false;
+    constexpr size_t f8_tap_stride = 4 * kTileM;                  // R is [item][25 taps][4 phases][128 pixels] fp32: one 128-byte line per warp and tap
+    auto f8_drain = [&]() {
+      // responses of phase tile f8_count - 1: this thread's pixel, taps 8 hf .. 8 hf + 7 (main + correction halves)
+      mbar_wait(f8_r_full, (f8_count - 1) & 1, wc, 7);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + C::F8_COL + 8 * hf;
+      uint32_t rm[8], rc[8];
+      if (DBG(8) || DBG(8192)) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { rm[t] = 0; rc[t] = 0; }
+      } else { tmem_ld8_nowait(taddr, rm); tmem_ld8_nowait(taddr + F8_NT, rc); }
+      tmem_ld_wait();
+      tc_fence_before();
+      if (f8_prev_valid) {
+        float* dst = prm.f8_out + f8_prev_off + (size_t)(8 * hf) * f8_tap_stride;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (8 * hf + t < 25) dst[(size_t)t * f8_tap_stride] = __fadd_rn(__uint_as_float(rm[t]), __uint_as_float(rc[t]));
+      }
+    };
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int txy = it % tiles_per_plane;
       const int p = it / tiles_per_plane;
@@ -351,7 +436,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&slot_empty[slot]);
+          // FUSE8: the slot of a phase's LAST chain is released only after the phase tile has been handed to the response GEMM
+          // (below), so that those MMAs queue behind two chains of the main loop instead of three
+          const bool f8_hold = FUSE8 && ch == nchains - 1;
+          if (lane == 0 && !f8_hold) mbar_arrive(&slot_empty[slot]);
 #pragma unroll
           for (int i = 0; i < HALF; ++i)
             acc[i] = __fadd_rn(acc[i], FAST ? __uint_as_float(vm[i]) : __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
@@ -377,7 +465,39 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = fminf(fmaxf(acc[i], 0.0f), 1.0f);
           }
-          if (COUT == 64 || prm.out_mode == TC_OUT_SPLIT) {
+          if (FUSE8 && DBG(2048)) {       // development: the layer without its fused tail
+            if (lane == 0) mbar_arrive(&slot_empty[(slot + SLOTS - 1) % SLOTS]);
+          } else if (FUSE8) {
+            uint32_t h[HALF / 2], l[HALF / 2];
+#pragma unroll
+            for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
+            // A tile row = this thread's pixel (its TMEM lane), 16-byte chunks 2 hf and 2 hf + 1 of the 128-byte row
+            const long long tf0 = TICK();
+            mbar_wait(f8_a_empty, (f8_count & 1) ^ 1, wc, 8);      // the previous tile's MMAs have read it
+            const long long tf1 = TICK(); t_f8_wait += tf1 - tf0;
+            const int row = lg * 32 + lane;
+            uint8_t* arow = smem + C::F8_A_OFF + row * 128;
+#pragma unroll
+            for (int q = 0; q < HALF / 8; ++q) {
+              if (DBG(32768)) break;
+              const int chunk = ((HALF / 8) * hf + q) ^ (row & 7);
+              *reinterpret_cast<uint4*>(arow + (chunk << 4)) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+              *reinterpret_cast<uint4*>(arow + C::F8_A_TILE + (chunk << 4)) = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const long long tf2 = TICK(); t_f8_st += tf2 - tf1;
+            if (f8_count) f8_drain();                             // the previous tile's responses leave TMEM before the next MMAs
+            t_f8_drain += TICK() - tf2;
+            f8_prev_off = ((size_t)it * 25 * 4 + j) * kTileM + row;
+            f8_prev_valid = !DBG(2) && !DBG(16384);               // pixels beyond the plane are written too (never read)
+            ++f8_count;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(f8_a_full);                             // the issuer warp takes it from here; nobody waits for it
+              mbar_arrive(&slot_empty[(slot + SLOTS - 1) % SLOTS]);   // the held slot of this phase's last chain
+            }
+          } else if (COUT == 64 || prm.out_mode == TC_OUT_SPLIT) {
             uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
             for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
@@ -459,7 +579,8 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         t_out += TICK() - to0;
       }
     }
-    if (prm.dbg_buf && lane == 0 && warp == kEpiWarp0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 3) * 8; o[0] = TICK() - t_begin; o[1] = tw_full; o[2] = t_ld; o[3] = t_out; }
+    if (FUSE8 && f8_count && !DBG(2048)) f8_drain();
+    if (prm.dbg_buf && lane == 0 && warp == kEpiWarp0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 3) * 8; o[0] = TICK() - t_begin; o[1] = tw_full; o[2] = t_ld; o[3] = t_out; o[4] = t_f8_wait; o[5] = t_f8_st; o[6] = t_f8_drain; }
   }
 
   tc_fence_before();
@@ -475,12 +596,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1, bool AHI = false>
+template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1, bool AHI = false, bool FUSE8 = false>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
-  using Cfg = PCfg<RB, NSPLIT, COUT>;
-  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL, AHI>;
+  using Cfg = PCfg<RB, NSPLIT, COUT, FUSE8>;
+  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL, AHI, FUSE8>;
   static unsigned long long attr_devices = 0;
   static int max_grid_of[64];                  // per device: CTAs that can be co-resident (persistent kernel: one wave)
   int dev = 0;
@@ -509,8 +630,8 @@ static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap&
   long long want = (items + CL - 1) / CL * CL;               // whole clusters
   const int grid = want < max_grid ? (int)want : max_grid;
   if (CL == 1) {
-    kern<<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
-    return cudaGetLastError();
+    return launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::SMEM_BYTES, stream, true, a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y,
+                         (int)items, error_flag);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
@@ -530,6 +651,11 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
     if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 128) return launch_patch_impl<128, 2, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     if (row_bytes == 64) return launch_patch_impl<64, 4, 64, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    return cudaErrorInvalidValue;
+  }
+  if (prm.f8_out) {                            // dconv7 handing its tiles to dconv8's response GEMM
+    if (row_bytes == 128 && prm.cout == 64 && prm.njobs == 4 && !prm.res_hi && prm.f8_w_hi && prm.f8_w_lo)
+      return launch_patch_impl<128, 4, 64, false, 1, false, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
     return cudaErrorInvalidValue;
   }
   if (prm.a_hi_only) {                         // dconv1 on the integer latent symbols

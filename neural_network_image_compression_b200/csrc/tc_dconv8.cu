@@ -66,6 +66,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = prm.N, Hi = prm.Hi, Wi = prm.Wi, Ho = 2 * prm.Hi, Wo = 2 * prm.Wi;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -82,6 +83,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_image = tiles_x * tiles_y;
 
@@ -271,7 +273,125 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   }
 }
 
+// ---- dconv8 behind the fused dconv7 (tc_conv_patch.cu, FUSE8): gather of the tap responses + colour inverse + pack ----------
+// R [3N][tile][25 taps][4 phases][128] fp32 holds, for every dconv7 OUTPUT pixel (y, x) = (2 iy + py, 2 ix + px) and tap t = 5a + b,
+// the response sum_ci x[y, x, ci] K8[a, b, 0, ci] (unscaled accumulator); (iy, ix) runs over dconv7's Hp x Wp INPUT grid, stored in
+// its 16 x 8-pixel tiles (row-major tile order, pixel m = 8 (iy % 16) + ix % 8 inside a tile), the order dconv7's epilogue
+// produces them in.  Conv2DTranspose(1, 5, 2, 'SAME') (decoder.py:17):
+//   out[2y + a - 1, 2x + b - 1] += R[y, x, 5a + b]
+// so every response feeds exactly one output pixel and the layer is a permutation-sum over R.  One block = one tile of one image,
+// one thread = one final row (4 pixels; RY = 0..3 = blockIdx.y, so the tap pattern is uniform in a block) of the 4 x 4 block of
+// final pixels under input pixel (iy, ix): 20 (even rows) or 30 (odd rows) 4-byte loads per colour plane, neighbouring threads on
+// neighbouring addresses, in the summation order of k_tc_dconv8's gather (taps a ascending, then b ascending), then bias, leaky,
+// clip (decoder.py:31-32), convert_to_rgb, clip, round(*255) (decoder.py:45-48) and one 12-byte run of RGB.
+template <int RY>
+__device__ __forceinline__ void dconv8_gather_row(const float* __restrict__ R, const TcDconv8Params& prm, int Hp, int Wp, int tiles_x,
+                                                  int tiles_per_plane, int n, int iy, int ix, bool rgb_aligned) {
+  constexpr int py = RY >> 1, fy = RY & 1;
+  constexpr int TILE_FLOATS = 25 * 4 * kTileM;
+  const int N = prm.N;
+  const int Ho = 4 * Hp, Wo = 4 * Wp;
+  // float offset of pixel (iy + dy, ix + dx) inside a plane's R block, or -1 outside the plane (contributes zero = SAME padding)
+  int noff[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int y = iy + dy, x = ix + dx;
+      const bool ok = y >= 0 && y < Hp && x >= 0 && x < Wp;
+      noff[dy + 1][dx + 1] = ok ? ((y >> 4) * tiles_x + (x >> 3)) * TILE_FLOATS + (y & 15) * kTileCols + (x & 7) : -1;
+    }
+  float outv[3][4];                                 // [colour plane][final column 0..3]
+#pragma unroll
+  for (int plane = 0; plane < 3; ++plane) {
+    const int set = plane == 0 ? 0 : 1;
+    const float inv_scale = prm.inv_scale[set], bias = prm.bias[set];
+    const float* Rp = R + (size_t)(plane * N + n) * tiles_per_plane * TILE_FLOATS;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+#pragma unroll
+      for (int fx = 0; fx < 2; ++fx) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int ta = (fy + 1) & 1; ta < 5; ta += 2) {
+          const int yy = py + (fy + 1 - ta) / 2;            // dconv7 output row relative to 2 iy: -1 .. 2
+          const int dy = yy < 0 ? -1 : (yy > 1 ? 1 : 0), npy = yy & 1;
+#pragma unroll
+          for (int tb = (fx + 1) & 1; tb < 5; tb += 2) {
+            const int xx = px + (fx + 1 - tb) / 2;
+            const int dx = xx < 0 ? -1 : (xx > 1 ? 1 : 0), npx = xx & 1;
+            const int o = noff[dy + 1][dx + 1];
+            const float r = o >= 0 ? __ldg(Rp + o + ((ta * 5 + tb) * 4 + npy * 2 + npx) * kTileM) : 0.0f;
+            acc = __fadd_rn(acc, r);
+          }
+        }
+        const float v = leaky(__fadd_rn(__fmul_rn(acc, inv_scale), bias));
+        outv[plane][2 * px + fx] = fminf(fmaxf(v, 0.0f), 1.0f);      // decoder.py:32
+      }
+    }
+  }
+  const int oy = 4 * iy + RY, ox0 = 4 * ix;
+  uint32_t packed[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int rx = 0; rx < 4; ++rx) {
+    const float y = outv[0][rx], cb = outv[1][rx], cr = outv[2][rx];
+    const size_t g = ((size_t)n * Ho + oy) * Wo + ox0 + rx;
+    if (prm.planes_out) {
+      const size_t plane_sz = (size_t)N * Ho * Wo;
+      prm.planes_out[g] = y; prm.planes_out[plane_sz + g] = cb; prm.planes_out[2 * plane_sz + g] = cr;
+    }
+    // convert_to_rgb: subtract the offsets, project with the inverse kernel, clip (decoder.py:45-46)
+    const float t0 = __fsub_rn(y, prm.cc.off[0]), t1 = __fsub_rn(cb, prm.cc.off[1]), t2 = __fsub_rn(cr, prm.cc.off[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float v = __fadd_rn(__fadd_rn(__fmul_rn(t0, prm.cc.kinv[k][0]), __fmul_rn(t1, prm.cc.kinv[k][1])),
+                                __fmul_rn(t2, prm.cc.kinv[k][2]));
+      const float c = fminf(fmaxf(v, 0.0f), 1.0f);
+      if (prm.prequant) prm.prequant[g * 3 + k] = c;
+      const uint32_t byte = (uint32_t)(uint8_t)rintf(__fmul_rn(c, 255.0f));                  // decoder.py:48
+      const int b = rx * 3 + k;
+      packed[b >> 2] |= byte << (8 * (b & 3));
+    }
+  }
+  if (prm.rgb) {
+    uint8_t* dst8 = prm.rgb + (((size_t)n * Ho + oy) * Wo + ox0) * 3;       // 12-byte runs: 4-byte aligned when the buffer is
+    if (rgb_aligned) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(dst8);
+      dst[0] = packed[0]; dst[1] = packed[1]; dst[2] = packed[2];
+    } else {
+#pragma unroll
+      for (int b = 0; b < 12; ++b) dst8[b] = (uint8_t)(packed[b >> 2] >> (8 * (b & 3)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTileM)
+k_dconv8_gather(const float* __restrict__ R, const __grid_constant__ TcDconv8Params prm, int Hp, int Wp, int tiles_x, int tiles_per_plane,
+                bool rgb_aligned) {
+  pdl_trigger();
+  pdl_wait();
+  const int n = blockIdx.x / tiles_per_plane, txy = blockIdx.x - n * tiles_per_plane;
+  const int iy = (txy / tiles_x) * kTileRows + (threadIdx.x >> 3), ix = (txy % tiles_x) * kTileCols + (threadIdx.x & 7);
+  if (iy >= Hp || ix >= Wp) return;
+  switch (blockIdx.y) {
+    case 0: dconv8_gather_row<0>(R, prm, Hp, Wp, tiles_x, tiles_per_plane, n, iy, ix, rgb_aligned); break;
+    case 1: dconv8_gather_row<1>(R, prm, Hp, Wp, tiles_x, tiles_per_plane, n, iy, ix, rgb_aligned); break;
+    case 2: dconv8_gather_row<2>(R, prm, Hp, Wp, tiles_x, tiles_per_plane, n, iy, ix, rgb_aligned); break;
+    default: dconv8_gather_row<3>(R, prm, Hp, Wp, tiles_x, tiles_per_plane, n, iy, ix, rgb_aligned); break;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_dconv8_gather(const float* R, const TcDconv8Params& prm, int Hp, int Wp, cudaStream_t stream) {
+  const int tiles_x = (Wp + kTileCols - 1) / kTileCols, tiles_y = (Hp + kTileRows - 1) / kTileRows;
+  const long long blocks = (long long)tiles_x * tiles_y * prm.N;
+  // a plane's R block is indexed with 32-bit float offsets
+  if (blocks <= 0 || blocks > 0x7fffffffLL || (long long)tiles_x * tiles_y * 12800 > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const bool rgb_aligned = (reinterpret_cast<uintptr_t>(prm.rgb) & 3) == 0;
+  return launch_kernel(k_dconv8_gather, dim3((unsigned)blocks, 4), dim3(kTileM), 0, stream, true, R, prm, Hp, Wp, tiles_x, tiles_x * tiles_y,
+                       rgb_aligned);
+}
 
 cudaError_t launch_tc_dconv8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                              const CUtensorMap& w_lo, const TcDconv8Params& prm, int num_sms, int* error_flag,
@@ -285,8 +405,8 @@ cudaError_t launch_tc_dconv8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, c
   const long long items = (long long)tiles_x * tiles_y * prm.N;
   if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = items < num_sms ? (int)items : num_sms;
-  k_tc_dconv8<<<grid, kThreads, SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items, error_flag);
-  return cudaGetLastError();
+  return launch_kernel(k_tc_dconv8, dim3(grid), dim3(kThreads), SMEM_BYTES, stream, true, a_hi, a_lo, w_hi, w_lo, prm, tiles_x, tiles_y, (int)items,
+                       error_flag);
 }
 
 }  // namespace nnic

@@ -519,6 +519,43 @@ def test_cluster_multicast_variant_is_bit_identical(nn, monkeypatch):
         assert np.array_equal(dec0(sym0), dec1(sym0)), shape
 
 
+def test_fused_dconv7_dconv8_is_bit_identical(nn, monkeypatch):
+    """The decoder's default path never writes dconv7's output: the layer's epilogue feeds dconv8's tap-response GEMM on chip
+    (tc_conv_patch.cu FUSE8) and k_dconv8_gather sums the responses (decoder.py:16-17,30-32,45-48).  It must give the bytes,
+    the pre-quantisation floats and the plane outputs of the unfused kernels (NNIC_FUSE_D78=0: dconv7 -> memory ->
+    k_tc_dconv8), on ragged tiles, one-pixel latents, several images and both weight sets."""
+    import torch
+    _, _, dY, dC = make_weights("spread")
+
+    def decoder():
+        d = nn.Decoder(0)
+        d.set_weights(0, dY); d.set_weights(1, dC)
+        return d
+    dec1 = decoder()
+    monkeypatch.setenv("NNIC_FUSE_D78", "0")
+    dec0 = decoder()
+    rng = np.random.default_rng(5)
+    for shape in ((1, 1, 1), (1, 9, 5), (3, 17, 33), (5, 8, 12), (2, 6, 9), (2, 64, 96)):
+        n, lh, lw = shape
+        sym = rng.integers(0, 256, size=(n, lh, lw, 96)).astype(np.uint8)
+        sym[rng.random(sym.shape) < 0.5] = 0
+        r0, p0 = dec0(sym, return_prequant=True)
+        r1, p1 = dec1(sym, return_prequant=True)
+        assert np.array_equal(r0, r1), shape
+        assert np.array_equal(p0, p1), shape
+        lat = [rng.random((n, lh, lw, 32)).astype(np.float32) for _ in range(3)]
+        for a, b in zip(dec0.run_model(lat), dec1.run_model(lat)):
+            assert np.array_equal(a, b), shape
+        # device buffers, output at an odd byte offset
+        xs = torch.from_numpy(sym).cuda()
+        buf = torch.zeros(n * 8 * lh * 8 * lw * 3 + 8, dtype=torch.uint8, device="cuda")
+        out = buf[1:1 + n * 8 * lh * 8 * lw * 3].view(n, 8 * lh, 8 * lw, 3)
+        dec1(xs, out=out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), r0), shape
+        assert int(buf[0]) == 0 and int(buf[-7:].sum()) == 0
+
+
 def test_bench_line_has_the_contract_keys():
     """`python bench.py` on one GPU: one JSON line with value, e2e (host copies counted), roofline, cpu_baseline, clocks and a
     positive launch count; the roofline kernel's share comes from the per-launch event timing."""
