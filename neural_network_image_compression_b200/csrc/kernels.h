@@ -142,6 +142,7 @@ struct TcPatchParams {
   int cout;                   // 64, or 32 (conv8)
   int fast;                   // one fp16 product per MAC, hi planes only (decoder, nnic_set_decode_precision)
   int cluster;                // 2: CTA pairs share every weight tile through TMA multicast; else 1
+  int pin;                    // nine-tap layers: seven weight tiles stay in shared memory for all items of a weight set (tc_conv_patch.cu PIN)
   int a_hi_only;              // the input is exact in its hi plane (integer latent symbols): no lo plane, no A_lo x W_hi product
   unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded (tc_common.cuh WaitCtx)
   int P, n_split;

@@ -88,6 +88,8 @@ struct nnic_handle {
   bool tc_dconv8 = true;            // dconv8 on the tensor cores (NNIC_TC_DCONV8=0: FFMA kernel)
   bool int_latent = true;           // dconv1 multiplies the integer symbols and folds /255 into its epilogue (NNIC_INT_LATENT=0: x/255 split in two planes)
   bool a_hi_only = false;           // set around dconv1's launch by decode_batch when its input is the integer symbol plane
+  int tc_pin = 1;                   // nine-tap layers keep seven of their weight tiles resident: 1 the residual layers conv4 / dconv6 (measured gain 6 %),
+                                    // 2 conv3 / dconv5 too (no gain there), 0 never (NNIC_TC_PIN)
   bool fuse_d78 = true;             // dconv7 feeds dconv8's response GEMM on chip (NNIC_FUSE_D78=0: dconv7's output goes through memory)
   float* fuse8_out = nullptr;       // set around dconv7's launch by decode_batch: the response tensor R it writes instead of its output
   EncodeTiledFn encode_tiled = nullptr;
@@ -651,6 +653,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.fast = (net == 1 && h->decode_fp16) ? 1 : 0;
     // tc_cluster: 0 never (default: no measurable gain, profiles/r1_cluster_multicast_ab.log), 1 residual layers only, 2 every layer
     pp.cluster = (!pp.fast && (h->tc_cluster == 2 || (h->tc_cluster == 1 && res))) ? 2 : 1;
+    pp.pin = (h->tc_pin == 2 || (h->tc_pin == 1 && res)) ? 1 : 0;
     pp.clamp01 = (net == 0 && gi == 3) ? 1 : 0;
     pp.out_u8 = out_u8; pp.out_prequant = out_prequant;
     pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
@@ -941,6 +944,7 @@ int nnic_create(int device, nnic_t** out) {
   if (const char* env = getenv("NNIC_TC_CONV1")) h->tc_conv1 = atoi(env) != 0;
   if (const char* env = getenv("NNIC_INT_LATENT")) h->int_latent = atoi(env) != 0;
   if (const char* env = getenv("NNIC_FUSE_D78")) h->fuse_d78 = atoi(env) != 0;
+  if (const char* env = getenv("NNIC_TC_PIN")) h->tc_pin = atoi(env);
   if (const char* env = getenv("NNIC_PDL")) nnic::g_pdl = atoi(env) != 0;    // process-wide
   if (const char* env = getenv("NNIC_TC_CLUSTER")) h->tc_cluster = atoi(env);
   if (const char* env = getenv("NNIC_TC_DBG")) h->tc_dbg = atoi(env);

@@ -105,13 +105,20 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t smem_addr, uint32_t s
 // A_lo x K8_hi per k-step, so the responses are bit-identical to the unfused path), and one phase later the epilogue warps move
 // the 25 responses per pixel from TMEM to global memory (tile-blocked, so a warp writes whole 128-byte lines): 100 bytes per
 // pixel instead of 256, read once by k_dconv8_gather.
-template <int RB, int NSPLIT, int COUT, bool FAST, int CL, bool AHI, bool FUSE8>
+template <int RB, int NSPLIT, int COUT, bool FAST, int CL, bool AHI, bool FUSE8, bool PIN>
 __global__ void __launch_bounds__((PCfg<RB, NSPLIT, COUT, FUSE8>::kThreads), 1)
 k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ TcPatchParams prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
   using C = PCfg<RB, NSPLIT, COUT, FUSE8>;
   static_assert(!FUSE8 || (RB == 128 && NSPLIT == 4 && COUT == 64 && !FAST && CL == 1 && !AHI), "FUSE8 is dconv7's variant");
+  static_assert(!PIN || (RB == 128 && COUT == 64 && !FAST && CL == 1 && !AHI && !FUSE8), "PIN is the variant of the nine-tap layers");
+  // PIN (conv3, conv4, dconv5, dconv6: one job of nine taps, one patch): seven of the nine weight tiles stay in their ring slots for
+  // all items of a weight set and only taps PIN_TA and PIN_TB stream through slot 7 -- 32 KB of weight fills per item instead of
+  // 144 KB.  The fills compete with the MMAs' operand reads for shared-memory bandwidth, which is what bounds these layers.
+  // Issuer 0 takes chains 0 and 2 (and with them every use of the shared slot, in order), issuer 1 takes chain 1.
+  constexpr int PIN_TA = 2, PIN_TB = 7, PIN_SHARED = 7;
+  auto pin_slot = [](int t) { return t < PIN_TA ? t : (t < PIN_TB ? t - 1 : t - 2); };
   constexpr int WSLOTS = C::WSLOTS;
   const WaitCtx wc{error_flag, prm.wait_timeout};
   constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
@@ -200,6 +207,91 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         __syncwarp();
         if (++pb == NSETS) { pb = 0; pphase ^= 1; }
       }
+    }
+  } else if (PIN && warp == 0) {
+    // ===================== TMA producer: pinned weight tiles + the two streamed taps =====================
+    int run = -1, cur_set = -1;
+    uint32_t su = 0;                           // fills of the shared slot so far
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int set = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
+      auto load_tap = [&](int t, int sl) {
+        uint8_t* wb = w_base + sl * W_SLOT;
+        mbar_expect_tx(&w_full[sl], W_SLOT);
+        const int wrow = set * prm.rows_per_set + prm.jobs[0].steps[t].w_row;
+        tma_load_2d(&map_w_hi, wb, &w_full[sl], 0, wrow);
+        tma_load_2d(&map_w_lo, wb + W_TILE, &w_full[sl], 0, wrow);
+      };
+      if (set != cur_set) {                    // first item, or the Y -> CbCr boundary: (re)load the pinned tiles
+        cur_set = set; ++run;
+        for (int t = 0; t < 9; ++t) {
+          if (t == PIN_TA || t == PIN_TB) continue;
+          const int sl = pin_slot(t);
+          if (run > 0) mbar_wait(&w_empty[sl], (uint32_t)(run - 1) & 1u, wc, 2);     // released after the previous set's last item
+          if (elect_one()) load_tap(t, sl);
+          __syncwarp();
+        }
+      }
+      for (int k = 0; k < 2; ++k, ++su) {
+        mbar_wait(&w_empty[PIN_SHARED], (su & 1u) ^ 1u, wc, 2);
+        if (elect_one()) load_tap(k ? PIN_TB : PIN_TA, PIN_SHARED);
+        __syncwarp();
+      }
+    }
+  } else if (PIN && warp < kEpiWarp0) {
+    // ===================== MMA issuers, pinned weights =====================
+    const int me = warp - 1;                   // 0: chains 0 and 2, 1: chain 1
+    constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
+    constexpr uint32_t idesc_narrow = make_idesc(COUT);
+    const uint32_t patch_u32 = smem_u32(patch_base), w_u32 = smem_u32(w_base);
+    int pb = 0; uint32_t pphase = 0;
+    int slot = 0; uint32_t slot_phase = 0;
+    int run = -1, cur_set = -1;
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int set = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
+      if (set != cur_set) { cur_set = set; ++run; }
+      const int nxt = it + (int)gridDim.x;
+      const bool last_of_run = nxt >= num_items || ((nxt / tiles_per_plane) < prm.n_split ? 0 : 1) != set;
+      mbar_wait(&patch_full[pb], pphase, wc, 3);
+      const uint32_t pset = patch_u32 + pb * SET_BYTES;
+      for (int ci = 0; ci < 3; ++ci) {
+        if ((ci == 1) != (me == 1)) {          // the other issuer's chain
+          if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+          continue;
+        }
+        uint32_t a_off[GTAPS];
+#pragma unroll
+        for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[0].steps[3 * ci + k].a_off;
+        mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
+        if (elect_one()) {
+          uint32_t accumulate = 0u;
+#pragma unroll
+          for (int k = 0; k < GTAPS; ++k) {
+            const int t = 3 * ci + k;
+            const bool stream = t == PIN_TA || t == PIN_TB;
+            const int w = stream ? PIN_SHARED : pin_slot(t);
+            mbar_wait(&w_full[w], stream ? (t == PIN_TB ? 1u : 0u) : ((uint32_t)run & 1u), wc, 5);
+            tc_fence_after();
+            const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO, C::LAYOUT);
+            const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
+            const uint64_t w_hl = make_desc_sbo(w_u32 + w * W_SLOT, C::W_SBO, C::LAYOUT);   // W_hi followed by W_lo
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              umma_f16(d_tmem, a_hi + 2 * ks, w_hl + 2 * ks, idesc_wide, accumulate);
+              umma_f16(d_tmem + COUT, a_lo + 2 * ks, w_hl + 2 * ks, idesc_narrow, 1u);
+              accumulate = 1u;
+            }
+            if (stream || last_of_run) umma_commit(&w_empty[w]);
+          }
+          umma_commit(&slot_full[slot]);
+        }
+        __syncwarp();
+        if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&patch_empty[pb]);        // every MMA of this issuer has read the patch
+      __syncwarp();
+      if (++pb == NSETS) { pb = 0; pphase ^= 1; }
     }
   } else if (warp == 0) {
     // ===================== TMA producer: weight groups =====================
@@ -602,12 +694,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
 uint32_t tc_patch_a_offset(int dy, int dx, int row_bytes) { return (uint32_t)(((dy + 1) * PW + (dx + 1)) * row_bytes); }
 
-template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1, bool AHI = false, bool FUSE8 = false>
+template <int RB, int NSPLIT, int COUT, bool FAST = false, int CL = 1, bool AHI = false, bool FUSE8 = false, bool PIN = false>
 static cudaError_t launch_patch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                      const CUtensorMap& w_lo, const TcPatchParams& prm, int num_sms, int* error_flag,
                                      cudaStream_t stream) {
   using Cfg = PCfg<RB, NSPLIT, COUT, FUSE8>;
-  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL, AHI, FUSE8>;
+  auto kern = k_tc_conv_patch<RB, NSPLIT, COUT, FAST, CL, AHI, FUSE8, PIN>;
   static unsigned long long attr_devices = 0;
   static int max_grid_of[64];                  // per device: CTAs that can be co-resident (persistent kernel: one wave)
   int dev = 0;
@@ -676,6 +768,10 @@ cudaError_t launch_tc_conv_patch(int row_bytes, const CUtensorMap& a_hi, const C
     return cudaErrorInvalidValue;
   }
   if (row_bytes == 128 && prm.cout == 32) return launch_patch_impl<128, 2, 32>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  if (prm.pin && row_bytes == 128 && prm.cout == 64 && prm.njobs == 1 && prm.npatch == 1 && prm.jobs[0].nsteps == 9) {   // nine-tap layers
+    if (heavy_epilogue) return launch_patch_impl<128, 4, 64, false, 1, false, false, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+    return launch_patch_impl<128, 2, 64, false, 1, false, false, true>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
+  }
   if (row_bytes == 128 && heavy_epilogue) return launch_patch_impl<128, 4, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   if (row_bytes == 128) return launch_patch_impl<128, 2, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);
   if (row_bytes == 64) return launch_patch_impl<64, 4, 64>(a_hi, a_lo, w_hi, w_lo, prm, num_sms, error_flag, stream);

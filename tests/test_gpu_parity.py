@@ -556,6 +556,30 @@ def test_fused_dconv7_dconv8_is_bit_identical(nn, monkeypatch):
         assert int(buf[0]) == 0 and int(buf[-7:].sum()) == 0
 
 
+def test_pinned_weight_tiles_are_bit_identical(nn, monkeypatch):
+    """The nine-tap layers (conv3, conv4, dconv5, dconv6) keep seven weight tiles in shared memory for all items of a weight
+    set and stream two (tc_conv_patch.cu PIN); NNIC_TC_PIN=0 streams every tile per item.  Same bytes, including CTAs whose
+    item sequence crosses the Y -> CbCr weight-set boundary and CTAs with a single item."""
+    eY, eC, dY, dC = make_weights("spread")
+
+    def codec():
+        e, d = nn.Encoder(0), nn.Decoder(0)
+        e.set_weights(0, eY); e.set_weights(1, eC); d.set_weights(0, dY); d.set_weights(1, dC)
+        return e, d
+    enc1, dec1 = codec()                       # default: the residual layers conv4 / dconv6
+    monkeypatch.setenv("NNIC_TC_PIN", "2")     # all four nine-tap layers
+    enc2, dec2 = codec()
+    monkeypatch.setenv("NNIC_TC_PIN", "0")
+    enc0, dec0 = codec()
+    for shape in ((1, 8, 8), (1, 72, 40), (3, 136, 264), (5, 256, 384), (2, 45, 67), (7, 128, 128)):
+        img = synthetic_images(*shape, seed=73)
+        sym0, r0 = enc0.encode_rate(img)
+        for e, d in ((enc1, dec1), (enc2, dec2)):
+            sym1, r1 = e.encode_rate(img)
+            assert np.array_equal(sym0, sym1) and np.array_equal(r0.hist, r1.hist), shape
+            assert np.array_equal(dec0(sym0), d(sym0)), shape
+
+
 def test_bench_line_has_the_contract_keys():
     """`python bench.py` on one GPU: one JSON line with value, e2e (host copies counted), roofline, cpu_baseline, clocks and a
     positive launch count; the roofline kernel's share comes from the per-launch event timing."""
