@@ -29,43 +29,6 @@ __device__ __forceinline__ void split2_scaled(float s0, float s1, uint32_t& hi2,
   const float f1 = __half2float(__ushort_as_half((unsigned short)(hi2 >> 16)));
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(s1 - f1), "f"(s0 - f0));
 }
-// ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): two IEEE round-to-nearest operations per instruction, bit-identical to
-// the scalar forms; the epilogues are bound by instruction issue, not by the fp32 lanes ----
-typedef unsigned long long f32x2_t;           // {low 32 bits: first value, high 32 bits: second value}
-__device__ __forceinline__ f32x2_t pack2(float a, float b) {
-  f32x2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2_t pack2u(uint32_t a, uint32_t b) {
-  f32x2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// split of a pair that already carries the factor ACT_SCALE (see split2_scaled): one packed subtraction for the two residuals
-__device__ __forceinline__ void split2_scaled_x2(f32x2_t s, uint32_t& hi2, uint32_t& lo2) {
-  float s0, s1;
-  unpack2(s, s0, s1);
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(s1), "f"(s0));
-  const float f0 = __half2float(__ushort_as_half((unsigned short)(hi2 & 0xffffu)));
-  const float f1 = __half2float(__ushort_as_half((unsigned short)(hi2 >> 16)));
-  float d0, d1;
-  unpack2(sub2(s, pack2(f0, f1)), d0, d1);
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(d1), "f"(d0));
-}
-// bias + leaky_relu of a pair: v = acc * scale + bias (one rounding: scale is a power of two), max(v, 0.2 v)
-__device__ __forceinline__ f32x2_t bias_leaky2(f32x2_t acc, f32x2_t scale, f32x2_t bias) {
-  const f32x2_t v = fma2(acc, scale, bias);
-  float v0, v1, t0, t1;
-  unpack2(v, v0, v1);
-  unpack2(mul2(v, pack2(LEAKY_ALPHA, LEAKY_ALPHA)), t0, t1);
-  return pack2(fmaxf(v0, t0), fmaxf(v1, t1));
-}
 __device__ __forceinline__ void split2_f32(float v0, float v1, uint32_t& hi2, uint32_t& lo2) {
   split2_scaled(v0 * ACT_SCALE, v1 * ACT_SCALE, hi2, lo2);
 }

@@ -145,6 +145,7 @@ struct TcPatchParams {
   int pin;                    // nine-tap layers: seven weight tiles stay in shared memory for all items of a weight set (tc_conv_patch.cu PIN)
   int a_hi_only;              // the input is exact in its hi plane (integer latent symbols): no lo plane, no A_lo x W_hi product
   unsigned long long wait_timeout;   // bound of a barrier wait in SM cycles, 0 = unbounded (tc_common.cuh WaitCtx)
+  int kernel_tag;             // reported with a timed-out wait: kernel id of the launch + 1 (NNIC_KERNEL_*)
   int P, n_split;
   int Hp, Wp;
   int Ho, Wo, out_stride;

@@ -37,6 +37,7 @@ inline const LayerSpec& spec_of(int set, int layer) { return set < 2 ? kEnc[laye
 inline const LayerSpec& gemm_spec(int net, int gi) { return net == 0 ? kEnc[gi + 1] : (net == 1 ? kDec[gi] : kEnt[gi]); }
 
 thread_local std::string g_global_error = "";
+thread_local const char* g_launch_ctx = "";    // layer whose launch is being enqueued (named in the error message of a failed launch)
 }  // namespace
 namespace nnic { int g_pdl = 1; }     // programmatic dependent launch between consecutive kernels (kernels.h launch_kernel; NNIC_PDL=0: off)
 namespace {
@@ -169,7 +170,7 @@ int fail(nnic_t* h, int code, const char* fmt, ...) {
 #define CK(h, call)                                                                                    \
   do {                                                                                                 \
     cudaError_t e__ = (call);                                                                          \
-    if (e__ != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    if (e__ != cudaSuccess) return fail(h, NNIC_ERR_CUDA, "%s failed: %s (%s:%d%s%s)", #call, cudaGetErrorString(e__), __FILE__, __LINE__, *g_launch_ctx ? ", " : "", g_launch_ctx); \
   } while (0)
 cudaEvent_t prof_event(nnic_t* h) {
   if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
@@ -568,7 +569,7 @@ int check_device_error(nnic_t* h) {
   if (h->error_flag_host && *h->error_flag_host != 0) {
     const int code = *h->error_flag_host;
     *h->error_flag_host = 0;
-    return fail(h, NNIC_ERR_CUDA, "a tensor-core kernel of an earlier call timed out in a barrier wait (code %d); the CUDA context is unusable", code);
+    return fail(h, NNIC_ERR_CUDA, "a tensor-core kernel of an earlier call timed out in a barrier wait (kernel %d, wait %d); the CUDA context is unusable", code / 100 - 1, code % 100);
   }
   return 0;
 }
@@ -659,6 +660,7 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     pp.hist = out_mode == TC_OUT_QUANT ? h->fused_hist : nullptr;
     pp.dbg = h->tc_dbg;
     pp.wait_timeout = h->wait_timeout;
+    pp.kernel_tag = kid + 1;
     pp.out_hi = out.hi; pp.out_lo = out.lo;
     pp.out_f32 = out_f32_planes ? out_f32_planes : out.f32;
     if (h->fuse8_out) { pp.f8_out = h->fuse8_out; pp.f8_w_hi = h->d8_w_hi; pp.f8_w_lo = h->d8_w_lo; }
@@ -669,8 +671,10 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
       CK(h, cudaMemsetAsync(h->tc_prof_buf, 0, prof_words * sizeof(long long), st));
       pp.dbg_buf = h->tc_prof_buf;
     }
+    g_launch_ctx = sp.name;
     CKL(h, kid, st,
         launch_tc_conv_patch(L.row_bytes, *pa_hi, *pa_lo, L.map_w_hi, L.map_w_lo, pp, h->num_sms, h->error_flag_dev, st));
+    g_launch_ctx = "";
     if (prof) {
       std::vector<long long> hb(prof_words);
       cudaStreamSynchronize(st);
@@ -957,7 +961,12 @@ int nnic_create(int device, nnic_t** out) {
   h->map_cache.reserve(64);
   e = cudaHostAlloc((void**)&h->error_flag_host, sizeof(int), cudaHostAllocMapped);
   if (e == cudaSuccess) { *h->error_flag_host = 0; e = cudaHostGetDevicePointer((void**)&h->error_flag_dev, h->error_flag_host, 0); }
-  if (e != cudaSuccess) { delete h; return fail(nullptr, NNIC_ERR_CUDA, "error flag allocation failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) {
+    // no mapped host memory (e.g. under CUDA_ENABLE_COREDUMP_ON_EXCEPTION): run without the timeout report; a timed-out wait still traps
+    if (h->error_flag_host) cudaFreeHost(h->error_flag_host);
+    h->error_flag_host = nullptr; h->error_flag_dev = nullptr;
+    cudaGetLastError();
+  }
   bool ok = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i)

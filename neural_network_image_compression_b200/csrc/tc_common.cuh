@@ -13,6 +13,7 @@ constexpr int kTileRows = 16, kTileCols = 8, kTileM = 128;
 struct WaitCtx {
   int* error_flag;
   unsigned long long timeout;
+  int tag;                     // reported with the code: 100 * tag + code (tag = kernel id of the launch, NNIC_KERNEL_* + 1)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const 
   const unsigned long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (wc.timeout && (unsigned long long)clock64() - t0 > wc.timeout) {
-      if (wc.error_flag) atomicExch(wc.error_flag, code);
+      if (wc.error_flag) atomicExch(wc.error_flag, 100 * wc.tag + code);
       __threadfence_system();
       __trap();
     }

@@ -106,7 +106,7 @@ template <int IN_KIND /*0 rgb u8, 1 f32 planes*/>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
   extern __shared__ uint8_t smem_raw[];
-  const WaitCtx wc{error_flag, prm.wait_timeout};
+  const WaitCtx wc{error_flag, prm.wait_timeout, 1};
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + W_OFF;
@@ -379,15 +379,19 @@ k_tc_conv1(const __grid_constant__ TcConv1Params prm, int tiles_x, int tiles_y, 
       const float inv16 = prm.inv_scale[set] * ACT_SCALE;
       const float4* bs4 = reinterpret_cast<const float4*>(bias_s + set * CO);
       uint32_t h[CO / 2], l[CO / 2];
-      const f32x2_t inv16x2 = pack2(inv16, inv16);
 #pragma unroll
       for (int i = 0; i < CO; i += 4) {
         const float4 b = bs4[i / 4];
-        // packed pairs: (main + correction) * 2^-k + bias, leaky, split -- the same roundings as the scalar forms
-        const f32x2_t a01 = add2(pack2u(vm[i], vm[i + 1]), pack2u(vc[i], vc[i + 1]));
-        const f32x2_t a23 = add2(pack2u(vm[i + 2], vm[i + 3]), pack2u(vc[i + 2], vc[i + 3]));
-        split2_scaled_x2(bias_leaky2(a01, inv16x2, pack2(b.x, b.y)), h[i / 2], l[i / 2]);
-        split2_scaled_x2(bias_leaky2(a23, inv16x2, pack2(b.z, b.w)), h[i / 2 + 1], l[i / 2 + 1]);
+        float v0 = fmaf(__fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])), inv16, b.x);
+        float v1 = fmaf(__fadd_rn(__uint_as_float(vm[i + 1]), __uint_as_float(vc[i + 1])), inv16, b.y);
+        float v2 = fmaf(__fadd_rn(__uint_as_float(vm[i + 2]), __uint_as_float(vc[i + 2])), inv16, b.z);
+        float v3 = fmaf(__fadd_rn(__uint_as_float(vm[i + 3]), __uint_as_float(vc[i + 3])), inv16, b.w);
+        v0 = fmaxf(v0, __fmul_rn(v0, LEAKY_ALPHA));
+        v1 = fmaxf(v1, __fmul_rn(v1, LEAKY_ALPHA));
+        v2 = fmaxf(v2, __fmul_rn(v2, LEAKY_ALPHA));
+        v3 = fmaxf(v3, __fmul_rn(v3, LEAKY_ALPHA));
+        split2_scaled(v0, v1, h[i / 2], l[i / 2]);
+        split2_scaled(v2, v3, h[i / 2 + 1], l[i / 2 + 1]);
       }
       // 32 channels = 64 bytes per fp16 plane: two 256-bit stores each (two full sectors per thread)
       const int y = it.ty * kTileRows + my, x = it.tx * kTileCols + mx;

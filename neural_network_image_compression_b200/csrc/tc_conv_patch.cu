@@ -120,7 +120,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   constexpr int PIN_TA = 2, PIN_TB = 7, PIN_SHARED = 7;
   auto pin_slot = [](int t) { return t < PIN_TA ? t : (t < PIN_TB ? t - 1 : t - 2); };
   constexpr int WSLOTS = C::WSLOTS;
-  const WaitCtx wc{error_flag, prm.wait_timeout};
+  const WaitCtx wc{error_flag, prm.wait_timeout, prm.kernel_tag};
   constexpr int kEpiWarps = C::kEpiWarps, kPatchWarp = C::kPatchWarp, kThreads = C::kThreads, SLOT_COLS = C::SLOT_COLS, SLOTS = C::SLOTS;
   constexpr int PATCH_TX = C::PATCH_TX, PATCH_SLOT = C::PATCH_SLOT, SET_BYTES = C::SET_BYTES, W_TILE = C::W_TILE, W_SLOT = C::W_SLOT,
                 BAR_OFF = C::BAR_OFF, KSTEPS = C::KSTEPS;
@@ -532,32 +532,26 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           // (below), so that those MMAs queue behind two chains of the main loop instead of three
           const bool f8_hold = FUSE8 && ch == nchains - 1;
           if (lane == 0 && !f8_hold) mbar_arrive(&slot_empty[slot]);
-          // packed fp32 pairs (common.cuh): the same round-to-nearest additions, half the instructions
 #pragma unroll
-          for (int i = 0; i < HALF; i += 2) {
-            const f32x2_t s2 = FAST ? pack2u(vm[i], vm[i + 1]) : add2(pack2u(vm[i], vm[i + 1]), pack2u(vc[i], vc[i + 1]));
-            unpack2(add2(pack2(acc[i], acc[i + 1]), s2), acc[i], acc[i + 1]);
-          }
+          for (int i = 0; i < HALF; ++i)
+            acc[i] = __fadd_rn(acc[i], FAST ? __uint_as_float(vm[i]) : __fadd_rn(__uint_as_float(vm[i]), __uint_as_float(vc[i])));
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
           t_ld += TICK() - te1;
         }
         const long long to0 = TICK();
         {
           // bias + leaky_relu in place (x*2^-k is exact, so the fused multiply-add rounds exactly like mul then add)
-          const f32x2_t sc2 = pack2(inv_scale, inv_scale);
 #pragma unroll
-          for (int i = 0; i < HALF; i += 2)
-            unpack2(bias_leaky2(pack2(acc[i], acc[i + 1]), sc2, pack2(bs[i], bs[i + 1])), acc[i], acc[i + 1]);
+          for (int i = 0; i < HALF; ++i) {
+            const float v = fmaf(acc[i], inv_scale, bs[i]);
+            acc[i] = fmaxf(v, __fmul_rn(v, LEAKY_ALPHA));
+          }
           if (has_res) {
             const __half* rh = reinterpret_cast<const __half*>(res_h);
             const __half* rl = reinterpret_cast<const __half*>(res_l);
-            const f32x2_t is2 = pack2(ACT_INV_SCALE, ACT_INV_SCALE);
 #pragma unroll
-            for (int i = 0; i < HALF; i += 2) {
-              f32x2_t r2 = pack2(__half2float(rh[i]), __half2float(rh[i + 1]));
-              if (!FAST) r2 = add2(r2, pack2(__half2float(rl[i]), __half2float(rl[i + 1])));     // join_f32: (hi + lo) / 16
-              unpack2(add2(pack2(acc[i], acc[i + 1]), mul2(r2, is2)), acc[i], acc[i + 1]);
-            }
+            for (int i = 0; i < HALF; ++i)
+              acc[i] = __fadd_rn(acc[i], FAST ? __half2float(rh[i]) * ACT_INV_SCALE : join_f32(rh[i], rl[i]));
           }
           if (COUT == 32 && prm.clamp01) {
 #pragma unroll
@@ -568,7 +562,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           } else if (FUSE8) {
             uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-            for (int i = 0; i < HALF; i += 2) split2_scaled_x2(mul2(pack2(acc[i], acc[i + 1]), pack2(ACT_SCALE, ACT_SCALE)), h[i / 2], l[i / 2]);
+            for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
             // A tile row = this thread's pixel (its TMEM lane), 16-byte chunks 2 hf and 2 hf + 1 of the 128-byte row
             const long long tf0 = TICK();
             mbar_wait(f8_a_empty, (f8_count & 1) ^ 1, wc, 8);      // the previous tile's MMAs have read it
@@ -598,7 +592,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           } else if (COUT == 64 || prm.out_mode == TC_OUT_SPLIT) {
             uint32_t h[HALF / 2], l[HALF / 2];
 #pragma unroll
-            for (int i = 0; i < HALF; i += 2) split2_scaled_x2(mul2(pack2(acc[i], acc[i + 1]), pack2(ACT_SCALE, ACT_SCALE)), h[i / 2], l[i / 2]);
+            for (int i = 0; i < HALF; i += 2) split2_f32(acc[i], acc[i + 1], h[i / 2], l[i / 2]);
             if (valid) {
 #pragma unroll
               for (int q = 0; q < HALF / 16; ++q) {

@@ -50,7 +50,7 @@ k_tc_dconv8(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
             const __grid_constant__ TcDconv8Params prm, int tiles_x, int tiles_y, int num_items, int* error_flag) {
   extern __shared__ uint8_t smem_raw[];
-  const WaitCtx wc{error_flag, prm.wait_timeout};
+  const WaitCtx wc{error_flag, prm.wait_timeout, 12};
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* w_base = smem + W_OFF;                               // [set][W_hi | W_lo]
