@@ -220,7 +220,9 @@ void nnic_colour_constants(float* k9, float* kinv9, float* off3);
 long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity);
 /* The tensor-core layers keep activations as two fp16 planes of v*16, which saturate at |v| > 4094 where the fp32
  * reference would carry on.  nnic_debug_saturated counts the saturated values in the activations of the most recent
- * encode and decode micro-batch (synchronises the device): 0 = the representation was exact to its ~22 bits. */
+ * encode and decode micro-batch (synchronises the device): 0 = the representation was exact to its ~22 bits.  The
+ * decoder's last activation (dconv7's output) exists on chip only in the default fused form and is counted when the
+ * handle was created with NNIC_FUSE_D78=0. */
 long long nnic_debug_saturated(nnic_t* h);
 
 #if defined(__GNUC__)

@@ -1569,7 +1569,8 @@ long long nnic_debug_fetch(nnic_t* h, int slot, float* out, long long capacity) 
 
 // The split-fp16 activation planes hold v * 16 and saturate at the fp16 maximum (|v| > 4094), where the fp32 reference would
 // carry on: a trained codec stays far below that (activations of O(1)), but nothing in the kernels reports it.  This debug
-// call counts the saturated values in the activations of the most recent encode (conv1 .. conv4) and decode (dconv1 .. dconv7)
+// call counts the saturated values in the activations of the most recent encode (conv1 .. conv4) and decode (dconv1 .. dconv6, and
+// dconv7 when its output is stored: NNIC_FUSE_D78=0)
 // micro-batch of the handle; 0 means the split representation was exact to its 22 bits everywhere.
 long long nnic_debug_saturated(nnic_t* h) {
   if (!h) return NNIC_ERR_INVALID_ARG;
