@@ -36,7 +36,8 @@ constexpr int kNumMma = 2;                     // MMA issuer warps (2 = alternat
 constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s), 4*NSPLIT epilogue warps, last warp patch TMA
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
-constexpr int GTAPS = 3;                                     // taps per accumulation chain
+constexpr int GTAPS = 3;                                     // taps per accumulation chain (12 k-steps) of the 64-channel inputs
+constexpr int GTAPS_K32 = 6;                                 // ... and of dconv1's 32-channel input (2 k-steps per tap: the same 12 k-steps)
 constexpr int TMEM_COLS = 512;
 constexpr int F8_NT = 32;                                    // FUSE8: dconv8's 25 taps padded to the MMA N granularity
 
@@ -344,6 +345,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else if (warp < kEpiWarp0) {
     // ===================== MMA issuer =====================
     const int my_parity = warp - 1;          // two issuers take alternate chains
+    constexpr int GT = RB == 64 ? GTAPS_K32 : GTAPS;
     int chain_ctr = 0;
     long long tw_patch = 0, tw_slot = 0, tw_w = 0, t_issue = 0, t_begin = TICK();
     constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
@@ -362,16 +364,16 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int sbeg = 0;
         for (int q = 0; q < seg; ++q) sbeg += prm.seg_steps[q];
         const int send = prm.npatch == 1 ? prm.jobs[j].nsteps : sbeg + prm.seg_steps[seg];
-        for (int s0 = sbeg; s0 < send; s0 += GTAPS) {          // one chain: <= GTAPS taps into one TMEM slot
-          const int ntaps = send - s0 < GTAPS ? send - s0 : GTAPS;
+        for (int s0 = sbeg; s0 < send; s0 += GT) {          // one chain: <= GTAPS taps into one TMEM slot
+          const int ntaps = send - s0 < GT ? send - s0 : GT;
           if (kNumMma == 2 && ((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
             ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
             continue;
           }
-          uint32_t a_off[GTAPS];
+          uint32_t a_off[GT];
 #pragma unroll
-          for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
+          for (int k = 0; k < GT; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
           if (active) { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 4); tw_slot += TICK() - t0; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
@@ -380,7 +382,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             uint32_t accumulate = 0u;
             int w = ws; uint32_t wp = wphase;
 #pragma unroll
-            for (int k = 0; k < GTAPS; ++k) {
+            for (int k = 0; k < GT; ++k) {
               if (k < ntaps) {
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
                 tc_fence_after();
