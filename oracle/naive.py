@@ -49,3 +49,46 @@ def conv2d_transpose_same_naive(x, kernel, bias, stride):
     _, pl, _ = same_pad(W * stride, kw, stride)
     out = full[:, pt:pt + stride * H, pl:pl + stride * W, :]
     return out + np.asarray(bias, np.float64)
+
+
+def dconv8_by_tap_responses(x, kernel, bias, tile_rows=16, tile_cols=8):
+    """Conv2DTranspose(1, 5, 2, 'SAME') (reference decoder.py:17) restated the way the CUDA decoder tail computes it
+    (csrc/tc_conv_patch.cu FUSE8 + csrc/tc_dconv8.cu k_dconv8_gather): x [n, 2Hp, 2Wp, Cin] is dconv7's output, addressed
+    as (y, x) = (2 iy + py, 2 ix + px) over dconv7's Hp x Wp input grid;
+      R[n][tile][t = 5a + b][phase = 2 py + px][m] = sum_ci x[n, y, x, ci] * K[a, b, 0, ci]
+    with tiles of tile_rows x tile_cols input-grid pixels in row-major order and m = tile_cols * (iy % tile_rows) + ix % tile_cols,
+    and every response feeds exactly one output pixel: out[2y + a - 1, 2x + b - 1] += R[y, x, 5a + b].
+    Returns (out [n, 4Hp, 4Wp, 1] before the activation, R).  Test infrastructure only."""
+    x = np.asarray(x, np.float64)
+    kernel = np.asarray(kernel, np.float64)
+    n, H2, W2, cin = x.shape
+    assert H2 % 2 == 0 and W2 % 2 == 0 and kernel.shape == (5, 5, 1, cin)
+    Hp, Wp = H2 // 2, W2 // 2
+    ty, tx = -(-Hp // tile_rows), -(-Wp // tile_cols)
+    R = np.zeros((n, ty * tx, 25, 4, tile_rows * tile_cols))
+    for iy in range(Hp):
+        for ix in range(Wp):
+            tile = (iy // tile_rows) * tx + ix // tile_cols
+            m = tile_cols * (iy % tile_rows) + ix % tile_cols
+            for py in range(2):
+                for px in range(2):
+                    v = x[:, 2 * iy + py, 2 * ix + px, :]                       # [n, cin]
+                    R[:, tile, :, 2 * py + px, m] = np.einsum("nc,abc->nab", v, kernel[:, :, 0, :]).reshape(n, 25)
+    out = np.zeros((n, 2 * H2, 2 * W2, 1))
+    for oy in range(2 * H2):
+        for ox in range(2 * W2):
+            acc = np.zeros(n)
+            for a in range((oy + 1) & 1, 5, 2):                                 # 2y + a - 1 = oy
+                y = (oy + 1 - a) // 2
+                if not 0 <= y < H2:
+                    continue
+                for b in range((ox + 1) & 1, 5, 2):
+                    xx = (ox + 1 - b) // 2
+                    if not 0 <= xx < W2:
+                        continue
+                    iy, py, ix, px = y // 2, y & 1, xx // 2, xx & 1
+                    tile = (iy // tile_rows) * tx + ix // tile_cols
+                    m = tile_cols * (iy % tile_rows) + ix % tile_cols
+                    acc += R[:, tile, 5 * a + b, 2 * py + px, m]
+            out[:, oy, ox, 0] = acc
+    return out + np.asarray(bias, np.float64), R

@@ -36,6 +36,25 @@ def test_conv_transpose_matches_naive(hw, ks):
     assert np.abs(got - ref).max() < 1e-12
 
 
+@pytest.mark.parametrize("hw", [(2, 2), (6, 10), (34, 18)])
+def test_dconv8_as_tap_responses_plus_gather(hw):
+    """The decoder tail of the CUDA path (dconv7's epilogue computes one response per (dconv7 output pixel, dconv8 tap), stored
+    tile-blocked; a gather kernel adds the responses that reach each output pixel) is the reference's
+    Conv2DTranspose(1, 5, 2, 'SAME') (decoder.py:17): checked here on the CPU against the two restatements of that layer,
+    including a grid that spans several 16 x 8 tiles with ragged edges."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, hw[0], hw[1], 5))
+    K = rng.standard_normal((5, 5, 1, 5))     # [kh,kw,Cout,Cin]
+    b = rng.standard_normal(1)
+    got, R = naive.dconv8_by_tap_responses(x, K, b)
+    assert got.shape == (2, 2 * hw[0], 2 * hw[1], 1)
+    assert np.abs(got - naive.conv2d_transpose_same_naive(x, K, b, 2)).max() < 1e-12
+    assert np.abs(got - O.conv2d_transpose_same(x, K, b, 2, "f64")).max() < 1e-12
+    # every response is used exactly once, except those whose output pixel lies outside the image (SAME cropping)
+    tiles = -(-(hw[0] // 2) // 16) * -(-(hw[1] // 2) // 8)
+    assert R.shape == (2, tiles, 25, 4, 128)
+
+
 def test_same_padding_rule():
     # k5 s2: even sizes pad (1,2), odd sizes (2,2); k3 s1: (1,1)
     assert O.same_pad(8, 5, 2) == (4, 1, 2)
