@@ -213,6 +213,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== TMA producer: pinned weight tiles + the two streamed taps =====================
     int run = -1, cur_set = -1;
     uint32_t su = 0;                           // fills of the shared slot so far
+    long long tw_w = 0, t_begin = TICK();
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int set = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
       auto load_tap = [&](int t, int sl) {
@@ -233,11 +234,12 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
       }
       for (int k = 0; k < 2; ++k, ++su) {
-        mbar_wait(&w_empty[PIN_SHARED], (su & 1u) ^ 1u, wc, 2);
+        { long long t0 = TICK(); mbar_wait(&w_empty[PIN_SHARED], (su & 1u) ^ 1u, wc, 2); tw_w += TICK() - t0; }
         if (elect_one()) load_tap(k ? PIN_TB : PIN_TA, PIN_SHARED);
         __syncwarp();
       }
     }
+    if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + 0) * 8; o[0] = TICK() - t_begin; o[1] = 0; o[2] = tw_w; }
   } else if (PIN && warp < kEpiWarp0) {
     // ===================== MMA issuers, pinned weights =====================
     const int me = warp - 1;                   // 0: chains 0 and 2, 1: chain 1
@@ -247,12 +249,13 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     int pb = 0; uint32_t pphase = 0;
     int slot = 0; uint32_t slot_phase = 0;
     int run = -1, cur_set = -1;
+    long long tw_patch = 0, tw_slot = 0, tw_w = 0, t_issue = 0, t_begin = TICK();
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int set = (it / tiles_per_plane) < prm.n_split ? 0 : 1;
       if (set != cur_set) { cur_set = set; ++run; }
       const int nxt = it + (int)gridDim.x;
       const bool last_of_run = nxt >= num_items || ((nxt / tiles_per_plane) < prm.n_split ? 0 : 1) != set;
-      mbar_wait(&patch_full[pb], pphase, wc, 3);
+      { long long t0 = TICK(); mbar_wait(&patch_full[pb], pphase, wc, 3); tw_patch += TICK() - t0; }
       const uint32_t pset = patch_u32 + pb * SET_BYTES;
       for (int ci = 0; ci < 3; ++ci) {
         if ((ci == 1) != (me == 1)) {          // the other issuer's chain
@@ -262,9 +265,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint32_t a_off[GTAPS];
 #pragma unroll
         for (int k = 0; k < GTAPS; ++k) a_off[k] = prm.jobs[0].steps[3 * ci + k].a_off;
-        mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 4);
+        { long long t0 = TICK(); mbar_wait(&slot_empty[slot], slot_phase ^ 1, wc, 4); tw_slot += TICK() - t0; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + slot * SLOT_COLS;
+        const long long ti0 = TICK();
         if (elect_one()) {
           uint32_t accumulate = 0u;
 #pragma unroll
@@ -272,7 +276,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int t = 3 * ci + k;
             const bool stream = t == PIN_TA || t == PIN_TB;
             const int w = stream ? PIN_SHARED : pin_slot(t);
-            mbar_wait(&w_full[w], stream ? (t == PIN_TB ? 1u : 0u) : ((uint32_t)run & 1u), wc, 5);
+            { long long t1 = TICK(); mbar_wait(&w_full[w], stream ? (t == PIN_TB ? 1u : 0u) : ((uint32_t)run & 1u), wc, 5); tw_w += TICK() - t1; }
             tc_fence_after();
             const uint64_t a_hi = make_desc_sbo(pset + a_off[k], A_SBO, C::LAYOUT);
             const uint64_t a_lo = a_hi + (uint64_t)(PATCH_SLOT >> 4);
@@ -288,12 +292,14 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           umma_commit(&slot_full[slot]);
         }
         __syncwarp();
+        t_issue += TICK() - ti0;
         if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
       }
       if (elect_one()) umma_commit(&patch_empty[pb]);        // every MMA of this issuer has read the patch
       __syncwarp();
       if (++pb == NSETS) { pb = 0; pphase ^= 1; }
     }
+    if (prm.dbg_buf && lane == 0) { long long* o = prm.dbg_buf + ((size_t)blockIdx.x * 4 + warp) * 8; o[0] = TICK() - t_begin; o[1] = tw_patch; o[2] = tw_slot; o[3] = tw_w; o[4] = t_issue; }
   } else if (warp == 0) {
     // ===================== TMA producer: weight groups =====================
     int ws = 0; uint32_t wphase = 0;
