@@ -628,8 +628,9 @@ int run_gemm_layer(nnic_t* h, int net, int gi, const Act& in, const Act& out, co
     for (int j = 0; j < L.njobs; ++j) {
       const TcJob& src = L.jobs[j];
       TcPatchJob& dst = pp.jobs[j];
-      // the patch kernel accumulates 12 k-steps per TMEM slot: three taps of a 64-channel input, six of dconv1's 32-channel input
-      const int gt = L.row_bytes == 64 ? 6 : 3;
+      // the patch kernel chains three taps per TMEM slot (tc_conv_patch.cu GTAPS / GTAPS_K32: the two issuers' chains must
+      // fit the 8-slot weight ring together)
+      const int gt = 3;
       dst.nsteps = src.nsteps; dst.nchains = (src.nsteps + gt - 1) / gt;
       dst.out_oy = src.out_oy; dst.out_ox = src.out_ox;
       for (int s = 0; s < src.nsteps; ++s) {

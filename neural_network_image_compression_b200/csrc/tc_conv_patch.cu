@@ -37,7 +37,10 @@ constexpr int kEpiWarp0 = 1 + kNumMma;        // warp 0 weight TMA, MMA issuer(s
 constexpr int PH = kTileRows + 2, PW = kTileCols + 2;        // 18 x 10 pixels
 constexpr int NSETS = 2;
 constexpr int GTAPS = 3;                                     // taps per accumulation chain (12 k-steps) of the 64-channel inputs
-constexpr int GTAPS_K32 = 6;                                 // ... and of dconv1's 32-channel input (2 k-steps per tap: the same 12 k-steps)
+constexpr int GTAPS_K32 = 3;                                 // ... and of dconv1's 32-channel input.  NOT 6 (the same 12 k-steps), although that saves the
+                                                             // epilogue four of nine chains: two issuers on alternate chains would then span 12 taps of the
+                                                             // 8-slot weight ring, and a parity wait on a slot whose previous fill has not landed yet is
+                                                             // satisfied by the fill before it (seen as one wrong dconv1 tile in ~1 of 400 4K decodes)
 constexpr int TMEM_COLS = 512;
 constexpr int F8_NT = 32;                                    // FUSE8: dconv8's 25 taps padded to the MMA N granularity
 
@@ -141,9 +144,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   uint64_t* f8_r_full = f8_a_empty + 1;        // FUSE8: the responses of a phase tile are in TMEM
   uint64_t* f8_a_full = f8_r_full + 1;         // FUSE8: every epilogue warp has written its rows of the A tile (and drained the previous responses)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f8_a_full + 1);
+  volatile int* tap_seen = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [kNumMma] highest tap whose weight fill an issuer has seen (RING_GUARD)
   float* bias_s = reinterpret_cast<float*>(smem + BAR_OFF + 512);
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(smem + C::HIST_OFF);
-  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS + 3) * 8 + 4 <= 512, "barrier area too small");
+  static_assert((2 * NSETS + 2 * WSLOTS + 2 * SLOTS + 3) * 8 + 4 + 8 <= 512, "barrier area too small");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,6 +158,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     for (int s = 0; s < WSLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&slot_full[a], 1); mbar_init(&slot_empty[a], kEpiWarps); }
     mbar_init(f8_a_empty, 1); mbar_init(f8_r_full, 1); mbar_init(f8_a_full, kEpiWarps);
+    tap_seen[0] = -1; tap_seen[1] = -1;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -352,6 +357,14 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== MMA issuer =====================
     const int my_parity = warp - 1;          // two issuers take alternate chains
     constexpr int GT = RB == 64 ? GTAPS_K32 : GTAPS;
+    // A parity wait tells the current phase of a barrier from the previous one only, so an issuer must not wait for fill n + 1 of
+    // a ring slot before fill n has been SEEN complete.  Two chains in flight span 2 * GT taps: inside the 8-slot ring that is
+    // automatic, FUSE8's 5-slot ring needs RING_GUARD: before an issuer waits for tap g it makes sure tap g - WSLOTS (same slot,
+    // previous fill) was observed -- by itself (own_hist) or by the other issuer (tap_seen[], written after each successful wait).
+    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;
+    static_assert(GT < WSLOTS && WSLOTS <= 8, "a chain must fit the weight ring");
+    int gtap = 0;                            // taps of all chains so far, in ring order
+    uint32_t own_hist = 0xffffffffu;         // bit j: tap gtap - 1 - j was this issuer's (history before the first tap counts as seen)
     int chain_ctr = 0;
     long long tw_patch = 0, tw_slot = 0, tw_w = 0, t_issue = 0, t_begin = TICK();
     constexpr uint32_t idesc_wide = make_idesc(2 * COUT);
@@ -374,6 +387,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           const int ntaps = send - s0 < GT ? send - s0 : GT;
           if (kNumMma == 2 && ((chain_ctr++) & 1) != my_parity) {            // the other issuer's chain: just advance the rings
             ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
+            gtap += ntaps; own_hist <<= ntaps;
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
             continue;
           }
@@ -390,7 +404,22 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int k = 0; k < GT; ++k) {
               if (k < ntaps) {
+                if (RING_GUARD) {
+                  const int g = gtap + k;
+                  if (g >= WSLOTS && !((own_hist >> (WSLOTS - 1 - k)) & 1u)) {
+                    const unsigned long long t0g = clock64();
+                    while (tap_seen[my_parity ^ 1] < g - WSLOTS) {
+                      if (wc.timeout && (unsigned long long)clock64() - t0g > wc.timeout) {
+                        if (wc.error_flag) atomicExch(wc.error_flag, 100 * wc.tag + 10);
+                        __threadfence_system();
+                        __trap();
+                      }
+                    }
+                    __threadfence_block();
+                  }
+                }
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
+                if (RING_GUARD) { __threadfence_block(); tap_seen[my_parity] = gtap + k; }
                 tc_fence_after();
                 if (active && !DBG(1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
@@ -418,6 +447,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           }
           __syncwarp();
           ws += ntaps; if (ws >= WSLOTS) { ws -= WSLOTS; wphase ^= 1; }
+          gtap += ntaps; own_hist = (own_hist << ntaps) | ((1u << ntaps) - 1u);
           t_issue += TICK() - ti0;
           if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
         }

@@ -44,7 +44,17 @@ def main():
         if ref is None:
             ref = out.clone()
         elif not torch.equal(ref, out):
-            print(f"iteration {i}: output differs from iteration 0 in {(ref != out).sum().item()} bytes", flush=True)
+            d = (ref != out)
+            idx = d.nonzero()
+            lo, hi = idx.min(dim=0).values.tolist(), idx.max(dim=0).values.tolist()
+            per_ch = d.sum(dim=(0, 1, 2)).tolist()
+            maxabs = (ref.to(torch.int16) - out.to(torch.int16)).abs().max().item()
+            print(f"iteration {i}: output differs from iteration 0 in {d.sum().item()} bytes: images {lo[0]}..{hi[0]}, rows {lo[1]}..{hi[1]}, "
+                  f"columns {lo[2]}..{hi[2]}, per RGB channel {per_ch}, max |difference| {maxabs}", flush=True)
+            out2 = torch.empty_like(out)
+            dec(lat, out=out2)
+            torch.cuda.synchronize()
+            print(f"   repeated once more: equals iteration 0: {torch.equal(out2, ref)}, equals the deviating output: {torch.equal(out2, out)}", flush=True)
             return 2
     print(f"{iters} iterations of {n}x{8 * lh}x{8 * lw} ok, identical bytes, {time.time() - t0:.1f} s", flush=True)
     return 0
