@@ -415,11 +415,10 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         __trap();
                       }
                     }
-                    __threadfence_block();
                   }
                 }
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
-                if (RING_GUARD) { __threadfence_block(); tap_seen[my_parity] = gtap + k; }
+                if (RING_GUARD) tap_seen[my_parity] = gtap + k;    // volatile shared-memory accesses of one thread stay in program order
                 tc_fence_after();
                 if (active && !DBG(1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
