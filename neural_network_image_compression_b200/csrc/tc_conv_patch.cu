@@ -358,10 +358,16 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const int my_parity = warp - 1;          // two issuers take alternate chains
     constexpr int GT = RB == 64 ? GTAPS_K32 : GTAPS;
     // A parity wait tells the current phase of a barrier from the previous one only, so an issuer must not wait for fill n + 1 of
-    // a ring slot before fill n has been SEEN complete.  Two chains in flight span 2 * GT taps: inside the 8-slot ring that is
-    // automatic, FUSE8's 5-slot ring needs RING_GUARD: before an issuer waits for tap g it makes sure tap g - WSLOTS (same slot,
-    // previous fill) was observed -- by itself (own_hist) or by the other issuer (tap_seen[], written after each successful wait).
-    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;
+    // a ring slot before fill n has been SEEN complete -- and with two issuers on alternate chains fill n may belong to the other
+    // one (8-slot ring, three-tap chains: taps T and T + 1 of a chain reuse the slots of taps T - 8 and T - 7 of the other issuer's
+    // last-but-one chain).  If that fill straggles while later ones land, the wait would pass on fill n - 1 and the MMAs would read a
+    // stale tile.  RING_GUARD: before an issuer waits for tap g it makes sure tap g - WSLOTS was observed -- by itself (own_hist) or
+    // by the other issuer (tap_seen[], written after each successful wait).  FUSE8's 5-slot ring needs it on every third tap.
+#ifdef NNIC_RING_GUARD_ALL
+    constexpr bool RING_GUARD = kNumMma > 1;              // measured: +6 % on the c2 step (profiles/r2_ring_guard_ab.log)
+#else
+    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;    // FUSE8 only; see DESIGN.md section 8 for the 8-slot rings
+#endif
     static_assert(GT < WSLOTS && WSLOTS <= 8, "a chain must fit the weight ring");
     int gtap = 0;                            // taps of all chains so far, in ring order
     uint32_t own_hist = 0xffffffffu;         // bit j: tap gtap - 1 - j was this issuer's (history before the first tap counts as seen)
