@@ -364,9 +364,18 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // stale tile.  RING_GUARD: before an issuer waits for tap g it makes sure tap g - WSLOTS was observed -- by itself (own_hist) or
     // by the other issuer (tap_seen[], written after each successful wait).  FUSE8's 5-slot ring needs it on every third tap.
 #ifdef NNIC_RING_GUARD_ALL
-    constexpr bool RING_GUARD = kNumMma > 1;              // measured: +6 % on the c2 step (profiles/r2_ring_guard_ab.log)
+    constexpr bool RING_GUARD = kNumMma > 1;              // before every tap, everywhere: measured +6 % on the c2 step (profiles/r2_ring_guard_ab.log)
 #else
-    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;    // FUSE8 only; see DESIGN.md section 8 for the 8-slot rings
+    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;    // before every tap: FUSE8
+#endif
+    // -DNNIC_RING_GUARD_CHAIN: the 8-slot rings check once per chain, before the TMEM-slot wait: the other issuer's observations
+    // are monotone, so the largest tap index the chain needs is enough, and the check is off the per-tap critical path.  Verified
+    // on the protocol model (tests/test_ring_model.py, guard "chain"); NOT yet run on a GPU (the round's GPU budget ended), hence
+    // not the default -- DESIGN.md section 8.
+#ifdef NNIC_RING_GUARD_CHAIN
+    constexpr bool RING_GUARD_CHAIN = kNumMma > 1 && !RING_GUARD;
+#else
+    constexpr bool RING_GUARD_CHAIN = false;
 #endif
     static_assert(GT < WSLOTS && WSLOTS <= 8, "a chain must fit the weight ring");
     int gtap = 0;                            // taps of all chains so far, in ring order
@@ -397,6 +406,22 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             if (++slot == SLOTS) { slot = 0; slot_phase ^= 1; }
             continue;
           }
+          if (RING_GUARD_CHAIN) {
+            int need = -1;
+#pragma unroll
+            for (int k = 0; k < GT; ++k)
+              if (k < ntaps && gtap + k >= WSLOTS && !((own_hist >> (WSLOTS - 1 - k)) & 1u)) need = gtap + k - WSLOTS;
+            if (need >= 0 && tap_seen[my_parity ^ 1] < need) {
+              const unsigned long long t0g = clock64();
+              while (tap_seen[my_parity ^ 1] < need) {
+                if (wc.timeout && (unsigned long long)clock64() - t0g > wc.timeout) {
+                  if (wc.error_flag) atomicExch(wc.error_flag, 100 * wc.tag + 10);
+                  __threadfence_system();
+                  __trap();
+                }
+              }
+            }
+          }
           uint32_t a_off[GT];
 #pragma unroll
           for (int k = 0; k < GT; ++k) a_off[k] = prm.jobs[j].steps[s0 + (k < ntaps ? k : 0)].a_off;
@@ -424,7 +449,7 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                   }
                 }
                 { long long t1 = TICK(); mbar_wait(&w_full[w], wp, wc, 5); tw_w += TICK() - t1; }
-                if (RING_GUARD) tap_seen[my_parity] = gtap + k;    // volatile shared-memory accesses of one thread stay in program order
+                if (RING_GUARD || RING_GUARD_CHAIN) tap_seen[my_parity] = gtap + k;    // volatile shared-memory accesses of one thread stay in program order
                 tc_fence_after();
                 if (active && !DBG(1)) {
                   const uint64_t a_hi = make_desc_sbo(pset + (a_off[k] & 0x7fffffffu), A_SBO, C::LAYOUT);
