@@ -366,7 +366,9 @@ k_tc_conv_patch(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #ifdef NNIC_RING_GUARD_ALL
     constexpr bool RING_GUARD = kNumMma > 1;              // before every tap, everywhere: measured +6 % on the c2 step (profiles/r2_ring_guard_ab.log)
 #else
-    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS;    // before every tap: FUSE8
+    // before every tap: FUSE8 (5-slot ring), and dconv1 (RB == 64): its taps are 2 k-steps, the shortest reuse distance of all
+    // layers, and it is the launch the packed-fp32 build failed in once its epilogue stopped throttling the issuers
+    constexpr bool RING_GUARD = kNumMma * GT > WSLOTS || RB == 64;
 #endif
     // -DNNIC_RING_GUARD_CHAIN: the 8-slot rings check once per chain, before the TMEM-slot wait: the other issuer's observations
     // are monotone, so the largest tap index the chain needs is enough, and the check is off the per-tap critical path.  Verified
